@@ -1,0 +1,350 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Harness that lets the reference's own, unmodified hot-path source files run in
+this container straight from ``/root/reference`` even though astropy, h5py,
+dask and matplotlib are not installed.  It is used ONLY by
+``tests/golden/make_golden.py`` (to generate the committed golden vectors) and
+by a handful of ``not gpu`` tests that are skipped when ``/root/reference`` is
+absent (it does not exist on the GPU box).
+
+What it does
+------------
+* registers empty package modules ``nuspacesim`` / ``.simulation`` /
+  ``.simulation.eas_optical`` / ... whose ``__path__`` points into the reference
+  tree, so that the reference's ``__init__`` files (which import everything,
+  including plotting and radio) never execute;
+* stubs ``dask.bag``, ``dask.diagnostics.progress``, ``matplotlib`` and the
+  handful of ``astropy`` names the hot path touches (``units``, ``constants``,
+  ``nddata.NDDataArray``, ``io.registry`` ...).  Only two astropy NUMBERS reach
+  the arithmetic: ``R_earth`` = 6378100 m and ``c`` = 299792458 m/s
+  (reference: simulation/geometry/region_geometry.py:51,
+  simulation/eas_optical/eas.py:71-79);
+* compiles the reference's one native file
+  ``simulation/eas_optical/src/zsteps.cpp`` in place (from where it lies under
+  /root/reference) into ``oracle/_ref/`` with the in-container pybind11;
+* fills ``Taus.pexit_grid`` / ``Taus.tau_cdf_grid`` with real ``NssGrid`` objects
+  read by this repo's pure-Python HDF5 reader.
+"""
+
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+import subprocess
+import sys
+import sysconfig
+import types
+
+import numpy as np
+
+REF_ROOT = os.environ.get("NSS_REFERENCE_ROOT", "/root/reference")
+REF_SRC = os.path.join(REF_ROOT, "src", "nuspacesim")
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_BUILD = os.path.join(HERE, "_ref")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(REF_SRC)
+
+
+# ----------------------------------------------------------------- zsteps build
+
+
+def build_zsteps(force: bool = False) -> str:
+    """g++ the reference's zsteps.cpp (pybind11) into oracle/_ref/."""
+    os.makedirs(REF_BUILD, exist_ok=True)
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    out = os.path.join(REF_BUILD, "zsteps" + suffix)
+    src = os.path.join(REF_SRC, "simulation", "eas_optical", "src", "zsteps.cpp")
+    if os.path.exists(out) and not force:
+        return out
+    import pybind11
+
+    cmd = [
+        "g++", "-O2", "-shared", "-std=c++17", "-fPIC",
+        "-I", pybind11.get_include(),
+        "-I", sysconfig.get_paths()["include"],
+        src, "-o", out,
+    ]
+    subprocess.check_call(cmd)
+    return out
+
+
+# ----------------------------------------------------------------- stubs
+
+
+class _Unit:
+    def __init__(self, name, dim, scale):
+        self.name, self.dim, self.scale = name, dim, scale
+
+    def __pow__(self, p):
+        return _Unit(f"{self.name}{p}", f"{self.dim}^{p}", self.scale**p)
+
+    def __repr__(self):
+        return self.name
+
+
+def _make_units():
+    u = types.ModuleType("astropy.units")
+    u.km = _Unit("km", "len", 1e3)
+    u.m = _Unit("m", "len", 1.0)
+    u.rad = _Unit("rad", "ang", 1.0)
+    u.deg = _Unit("deg", "ang", np.pi / 180.0)
+    u.MHz = _Unit("MHz", "freq", 1e6)
+    u.Hz = _Unit("Hz", "freq", 1.0)
+    u.dB = _Unit("dB", "db", 1.0)
+    u.s = _Unit("s", "time", 1.0)
+    u.Unit = _Unit
+    table = {
+        "km": u.km, "m": u.m, "rad": u.rad, "deg": u.deg, "MHz": u.MHz,
+        "Hz": u.Hz, "dB": u.dB, "m2": u.m**2, "s": u.s,
+    }
+
+    class Quantity:
+        def __init__(self, value, unit=None):
+            if isinstance(value, Quantity):
+                self.value, self.unit = value.value, value.unit
+            elif isinstance(value, str):
+                parts = value.split()
+                self.value = float(parts[0])
+                self.unit = table[parts[1]] if len(parts) > 1 else unit
+            else:
+                self.value, self.unit = value, unit
+
+        def to(self, unit):
+            if self.unit is None or self.unit.scale == unit.scale:
+                return Quantity(self.value, unit)
+            return Quantity(self.value * (self.unit.scale / unit.scale), unit)
+
+        def __str__(self):
+            return f"{self.value} {self.unit}"
+
+    u.Quantity = Quantity
+    return u
+
+
+def _install_stubs():
+    if "astropy" in sys.modules and getattr(sys.modules["astropy"], "_nss_stub", False):
+        return
+    # never shadow a real installation
+    for real in ("astropy", "dask", "matplotlib"):
+        if real not in sys.modules and importlib.util.find_spec(real) is not None:
+            raise RuntimeError(f"{real} is installed; the stub harness is not needed")
+
+    astropy = types.ModuleType("astropy")
+    astropy._nss_stub = True
+    astropy.__path__ = []
+    units = _make_units()
+    constants = types.ModuleType("astropy.constants")
+    constants.R_earth = units.Quantity(6378100.0, units.m)  # IAU 2015 nominal
+    constants.c = units.Quantity(299792458.0, units.m)  # SI (m/s); .value is used
+    time = types.ModuleType("astropy.time")
+    time.TimeDelta = time.Time = object
+    coordinates = types.ModuleType("astropy.coordinates")
+    for n in ("AltAz", "EarthLocation", "SkyCoord", "get_body", "get_sun", "get_moon"):
+        setattr(coordinates, n, object)
+    nddata = types.ModuleType("astropy.nddata")
+
+    class NDDataArray:
+        def __init__(self, data, *a, **k):
+            self._data = np.asarray(data)
+
+        @property
+        def data(self):
+            return self._data
+
+        @property
+        def ndim(self):
+            return self._data.ndim
+
+        @property
+        def shape(self):
+            return self._data.shape
+
+        @property
+        def dtype(self):
+            return self._data.dtype
+
+    nddata.NDDataArray = NDDataArray
+    io = types.ModuleType("astropy.io")
+    io.__path__ = []
+    registry = types.ModuleType("astropy.io.registry")
+
+    class UnifiedReadWrite:
+        def __init__(self, instance, cls, kind):
+            self._instance, self._cls = instance, cls
+
+    class UnifiedReadWriteMethod(property):
+        def __init__(self, func):
+            super().__init__()
+            self._f = func
+
+        def __get__(self, instance, owner=None):
+            return self._f(instance, owner)
+
+    registry.UnifiedReadWrite = UnifiedReadWrite
+    registry.UnifiedReadWriteMethod = UnifiedReadWriteMethod
+    registry.register_reader = registry.register_writer = lambda *a, **k: None
+    registry.register_identifier = lambda *a, **k: None
+    registry.read = registry.write = lambda *a, **k: (_ for _ in ()).throw(
+        NotImplementedError("astropy registry is stubbed")
+    )
+    fits = types.ModuleType("astropy.io.fits")
+    fits.connect = types.SimpleNamespace(is_fits=lambda *a, **k: False)
+    misc = types.ModuleType("astropy.io.misc")
+    misc.__path__ = []
+    hdf5 = types.ModuleType("astropy.io.misc.hdf5")
+    hdf5.is_hdf5 = lambda *a, **k: False
+    misc.hdf5 = hdf5
+    table = types.ModuleType("astropy.table")
+    table.Table = dict
+    io.fits, io.registry, io.misc = fits, registry, misc
+    astropy.units, astropy.constants, astropy.time = units, constants, time
+    astropy.coordinates, astropy.nddata, astropy.io, astropy.table = (
+        coordinates, nddata, io, table,
+    )
+    mods = {
+        "astropy": astropy, "astropy.units": units, "astropy.constants": constants,
+        "astropy.time": time, "astropy.coordinates": coordinates,
+        "astropy.nddata": nddata, "astropy.io": io, "astropy.io.registry": registry,
+        "astropy.io.fits": fits, "astropy.io.misc": misc,
+        "astropy.io.misc.hdf5": hdf5, "astropy.table": table,
+    }
+
+    # dask: sequential stand-in for bag.from_sequence(...).map(f).compute()
+    dask = types.ModuleType("dask")
+    dask.__path__ = []
+    bag = types.ModuleType("dask.bag")
+
+    class _Bag:
+        def __init__(self, seq):
+            self.seq, self.f = list(seq), None
+
+        def map(self, f):
+            self.f = f
+            return self
+
+        def compute(self):
+            return [self.f(x) for x in self.seq]
+
+    bag.from_sequence = lambda seq, partition_size=None: _Bag(seq)
+    diag = types.ModuleType("dask.diagnostics")
+    diag.__path__ = []
+    prog = types.ModuleType("dask.diagnostics.progress")
+
+    class ProgressBar:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    prog.ProgressBar = ProgressBar
+    diag.progress = prog
+    dask.bag, dask.diagnostics = bag, diag
+    mods.update({
+        "dask": dask, "dask.bag": bag, "dask.diagnostics": diag,
+        "dask.diagnostics.progress": prog,
+    })
+
+    class _Anything(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Anything(self.__name__ + "." + name)
+
+        def __call__(self, *a, **k):
+            return self
+
+    for n in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm",
+              "mpl_toolkits", "mpl_toolkits.axes_grid1"):
+        m = _Anything(n)
+        m.__path__ = []
+        mods[n] = m
+    sys.modules.update(mods)
+
+
+def _pkg(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path] if isinstance(path, str) else list(path)
+    m.__package__ = name
+    sys.modules[name] = m
+    return m
+
+
+_LOADED = {}
+
+
+def load_reference():
+    """Import the reference hot-path modules; returns a namespace of them."""
+    if _LOADED:
+        return types.SimpleNamespace(**_LOADED)
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    if "nuspacesim" in sys.modules and not getattr(sys.modules["nuspacesim"], "_nss_stub", False):
+        raise RuntimeError("a real nuspacesim is already imported")
+    _install_stubs()
+    build_zsteps()
+    root = _pkg("nuspacesim", REF_SRC)
+    root._nss_stub = True
+    _pkg("nuspacesim.utils", os.path.join(REF_SRC, "utils"))
+    _pkg("nuspacesim.simulation", os.path.join(REF_SRC, "simulation"))
+    _pkg("nuspacesim.simulation.geometry", os.path.join(REF_SRC, "simulation", "geometry"))
+    _pkg("nuspacesim.simulation.taus", os.path.join(REF_SRC, "simulation", "taus"))
+    _pkg("nuspacesim.simulation.spectra", os.path.join(REF_SRC, "simulation", "spectra"))
+    _pkg("nuspacesim.simulation.atmosphere", os.path.join(REF_SRC, "simulation", "atmosphere"))
+    _pkg(
+        "nuspacesim.simulation.eas_optical",
+        [os.path.join(REF_SRC, "simulation", "eas_optical"), REF_BUILD],
+    )
+    _pkg("nuspacesim.data", os.path.join(REF_SRC, "data"))
+    # too.py needs real ephemerides; RegionGeom never calls it
+    too = types.ModuleType("nuspacesim.simulation.geometry.too")
+    too.ToOEvent = object
+    sys.modules[too.__name__] = too
+    imp = importlib.import_module
+    _LOADED.update(
+        config=imp("nuspacesim.config"),
+        grid=imp("nuspacesim.utils.grid"),
+        cdf=imp("nuspacesim.utils.cdf"),
+        interp=imp("nuspacesim.utils.interp"),
+        region_geometry=imp("nuspacesim.simulation.geometry.region_geometry"),
+        spectra=imp("nuspacesim.simulation.spectra.spectra"),
+        taus=imp("nuspacesim.simulation.taus.taus"),
+        eas=imp("nuspacesim.simulation.eas_optical.eas"),
+        cphotang=imp("nuspacesim.simulation.eas_optical.cphotang"),
+        shower_properties=imp("nuspacesim.simulation.eas_optical.shower_properties"),
+        detector_geometry=imp("nuspacesim.simulation.eas_optical.detector_geometry"),
+    )
+    return types.SimpleNamespace(**_LOADED)
+
+
+def read_ref_grid(ref, relpath):
+    """Read one of the reference's NssGrid HDF5 tables into a reference NssGrid."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from nuspacesim_b200.utils.hdf5_min import H5File
+
+    f = H5File(os.path.join(REF_SRC, "data", relpath))
+    data = f["__nss_grid_data__"][()]
+    names = [f.attrs[f"AXIS{i}"] for i in range(data.ndim)]
+    axes = [f["__nss_grid_axes__"][n][()] for n in names]
+    return ref.grid.NssGrid(data, axes=axes, axis_names=names)
+
+
+def make_taus(ref, config):
+    """Construct the reference ``Taus`` without going through NssGrid.read."""
+    t = ref.taus.Taus.__new__(ref.taus.Taus)
+    t.config = config
+    tid = config.simulation.tau_shower.id
+    ver = config.simulation.tau_shower.table_version
+    t.pexit_grid = read_ref_grid(ref, f"{tid}_tables/nu2tau_pexit.{ver}.h5")
+    t.tau_cdf_grid = read_ref_grid(ref, f"{tid}_tables/nu2tau_cdf.{ver}.h5")
+    return t
+
+
+def default_config(ref, **sim_overrides):
+    cfg = ref.config.config_from_toml(os.path.join(REF_ROOT, "sample_input_file.toml"))
+    for k, v in sim_overrides.items():
+        setattr(cfg.simulation, k, v)
+    return cfg

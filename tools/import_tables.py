@@ -1,0 +1,43 @@
+"""Re-encode the nu2tau NssGrid tables (scientific input data, nupyprop /
+nuleptonsim outputs) into this package's data directory through this repo's own
+HDF5 writer.  Layout per file (reference: src/nuspacesim/utils/grid.py:314-359):
+root attrs AXIS0..AXISn, dataset ``__nss_grid_data__``, group ``__nss_grid_axes__``.
+
+    python tools/import_tables.py /root/reference/src/nuspacesim/data
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nuspacesim_b200.utils.hdf5_min import H5File, write_hdf5  # noqa: E402
+
+
+def main(src):
+    dst = os.path.join(ROOT, "nuspacesim_b200", "data")
+    for d in ("nupyprop_tables", "nupyprop_bdhm_tables", "nuleptonsim_tables"):
+        os.makedirs(os.path.join(dst, d), exist_ok=True)
+        for fn in sorted(os.listdir(os.path.join(src, d))):
+            if not fn.endswith(".h5"):
+                continue
+            f = H5File(os.path.join(src, d, fn))
+            data = np.asarray(f["__nss_grid_data__"][()])
+            names = [f.attrs[f"AXIS{i}"] for i in range(data.ndim)]
+            axes = {n: np.asarray(f["__nss_grid_axes__"][n][()]) for n in names}
+            write_hdf5(
+                os.path.join(dst, d, fn),
+                {"__nss_grid_data__": data,
+                 "__nss_grid_axes__": {"__kind__": "group", "members": axes, "attrs": {}}},
+                {f"AXIS{i}": n for i, n in enumerate(names)},
+            )
+            g = H5File(os.path.join(dst, d, fn))
+            assert np.array_equal(g["__nss_grid_data__"][()], data)
+            for n in names:
+                assert np.array_equal(g["__nss_grid_axes__"][n][()], axes[n])
+            print(d, fn, data.shape, names)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
