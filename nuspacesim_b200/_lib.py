@@ -1,0 +1,192 @@
+"""ctypes binding of libnss_b200.so (C ABI declared in include/nss_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, the
+operators raise.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnss_b200.so")
+
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+c_u64p = C.POINTER(C.c_ulonglong)
+
+FLAG_LOGE_RANGE = 1
+FLAG_U_RANGE = 2
+
+
+class NssParams(C.Structure):
+    """Mirror of ``struct NssParams`` (include/nss_b200.h)."""
+
+    _fields_ = [
+        ("detector_altitude", C.c_double),
+        ("det_lat", C.c_double),
+        ("det_long", C.c_double),
+        ("max_cherenkov_angle", C.c_double),
+        ("max_azimuth_angle", C.c_double),
+        ("angle_from_limb", C.c_double),
+        ("telescope_effective_area", C.c_double),
+        ("quantum_efficiency", C.c_double),
+        ("photo_electron_threshold", C.c_double),
+        ("etau_frac", C.c_double),
+        ("spectrum_kind", C.c_int32),
+        ("has_cloud", C.c_int32),
+        ("log_nu_energy", C.c_double),
+        ("spec_index", C.c_double),
+        ("spec_lower", C.c_double),
+        ("spec_upper", C.c_double),
+        ("cloud_top", C.c_double),
+        ("earth_radius", C.c_double),
+        ("core_alt", C.c_double),
+        ("min_los", C.c_double),
+        ("max_los", C.c_double),
+        ("sin_max_theta", C.c_double),
+        ("max_phi_s", C.c_double),
+        ("min_phi_s", C.c_double),
+        ("mcnorm", C.c_double),
+    ]
+
+
+GEOM_FIELDS = (
+    "thetaTrSubV", "costhetaTrSubV", "phiTrSubV", "phiS", "losPathLen", "thetaS",
+    "costhetaNSubV", "costhetaTrSubN", "betaTrSubN", "latS", "longS", "elevAngVSubN",
+    "aziAngVSubN",
+)
+
+
+class NssGeomSoA(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in GEOM_FIELDS] + [("event_mask", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/nss_b200.h declares
+SIGNATURES = {
+    "nss_params_init": (C.c_int, [C.POINTER(NssParams)]),
+    "nss_tables_create": (C.c_int, [c_f64p, c_f64p, C.c_int, c_f64p, C.c_int, c_f64p, c_f64p,
+                                    C.c_int, c_f64p, C.c_int, c_f64p, C.c_int,
+                                    C.POINTER(C.c_void_p)]),
+    "nss_tables_free": (None, [C.c_void_p]),
+    "nss_geom_throw_u": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_int64,
+                                   C.POINTER(NssGeomSoA), C.c_void_p]),
+    "nss_geom_throw_philox": (C.c_int, [C.POINTER(NssParams), C.c_uint64, C.c_uint64, C.c_int64,
+                                        C.POINTER(NssGeomSoA), C.c_void_p]),
+    "nss_scan_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "nss_mask_scan": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "nss_compact_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_int, C.c_void_p]),
+    "nss_geom_lat_long": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 7 + [C.c_int64] +
+                          [C.c_void_p] * 3),
+    "nss_spectrum_powerlaw": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_void_p]),
+    "nss_tau_exit_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "nss_tau_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nss_tau_sample": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
+    "nss_alt_dec": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3),
+    "nss_eas_optical": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 4 + [C.c_int64] +
+                        [C.c_void_p] * 6),
+    "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 3 + [C.c_int64] +
+                     [C.c_void_p] * 4),
+    "nss_mc_workspace_bytes": (C.c_int64, []),
+    "nss_mcintegral": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 7 +
+                       [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double] +
+                       [C.c_void_p] * 3),
+    "nss_acceptance_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "nss_run_acceptance": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_uint64, C.c_uint64,
+                                     C.c_int64, C.c_int64] + [C.c_void_p] * 5),
+    "nss_acceptance_finalize": (C.c_int, [C.POINTER(NssParams), c_f64p, c_f64p]),
+    "nss_philox4x32": (None, [C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "nss_strerror": (C.c_char_p, [C.c_int]),
+    "nss_version": (C.c_int, []),
+}
+
+_LIB = None
+
+
+class NssLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library (build it first with ``python -m nuspacesim_b200.build``)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise NssLibraryError(
+                f"{LIB_PATH} not found: build it with `python -m nuspacesim_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the hot path."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().nss_strerror(rc).decode()
+        raise NssLibraryError(f"libnss_b200 {what} failed: {msg} (code {rc})")
+
+
+# ------------------------------------------------------------------ device plumbing (torch)
+
+
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise NssLibraryError(
+            "no CUDA device visible: the nuspacesim_b200 operators run only on a GPU "
+            "(there is no CPU fallback)"
+        )
+    return torch
+
+
+def stream_ptr() -> C.c_void_p:
+    torch = torch_cuda()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def is_device_array(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def to_device(x, dtype="float64"):
+    """NumPy array / scalar sequence / torch tensor -> contiguous CUDA tensor."""
+    torch = torch_cuda()
+    td = getattr(torch, dtype)
+    if hasattr(x, "is_cuda"):
+        return x.to(device="cuda", dtype=td).contiguous()
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return torch.from_numpy(a).to("cuda", non_blocking=False)
+
+
+def empty(n, dtype="float64"):
+    torch = torch_cuda()
+    return torch.empty(int(n), dtype=getattr(torch, dtype), device="cuda")
+
+
+def zeros(n, dtype="float64"):
+    torch = torch_cuda()
+    return torch.zeros(int(n), dtype=getattr(torch, dtype), device="cuda")
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_host(t) -> np.ndarray:
+    return t.detach().cpu().numpy()

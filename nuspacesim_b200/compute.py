@@ -1,0 +1,196 @@
+"""compute(): one simulation of the optical hot path, stage by stage.
+
+Mirror of ``nuspacesim.compute`` (src/nuspacesim/compute.py:73-298) for the optical
+branch: same signature, the same 15 result columns in the same order, the same meta keys
+(``OMCINT``, ``OMCINTGO``, ``ONEVPASS``, ``OMCINTUN``, ``simTime``, ``HIERARCH Config``).
+All stage arrays stay on the GPU between stages; columns are copied to the host once
+each for the returned table.  The radio branch (compute.py:261-294) is out of scope and
+is skipped.
+
+``run_acceptance`` is the column-free mode used for large N: the whole chain runs from
+in-kernel Philox (``nss_run_acceptance``) and only 8 doubles leave the GPU; with
+torch.distributed initialised the thrown-event range is split across ranks and the sums
+are all-reduced (the only exchange step on the path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Iterable
+
+import numpy as np
+
+from . import _lib, results_table
+from .params import params_from_config
+from .simulation.atmosphere.clouds import CloudTopHeight
+from .simulation.eas_optical.eas import EAS
+from .simulation.geometry.region_geometry import RegionGeom
+from .simulation.spectra.spectra import Spectra
+from .simulation.taus.taus import Taus
+
+__all__ = ["compute", "run_acceptance"]
+
+
+def compute(config, verbose: bool = False, output_file: str = None, to_plot: list = [],
+            write_stages: bool = False, seed: int = 0, uniforms: dict = None):
+    """Simulate an upward going shower (compute.py:73-298, optical branch).
+
+    Extensions: ``seed`` keys the Philox streams (the reference uses the global unseeded
+    NumPy state); ``uniforms`` may hold pre-sampled arrays ``u4`` (4, N), ``u_spec``,
+    ``u_tau``, ``u_dec`` (N,) indexed by thrown event, for shared-input validation.
+    """
+
+    def logv(*args):
+        if verbose:
+            print(*args)
+
+    sim = results_table.init(config)
+    geom = RegionGeom(config, seed=seed)
+    cloud = CloudTopHeight(config)
+    spec = Spectra(config, seed=seed)
+    tau = Taus(config, seed=seed)
+    eas = EAS(config, seed=seed)
+    if config.simulation.mode == "Target":
+        raise NotImplementedError("Target (ToO) mode is outside the accelerated path")
+
+    class StagedWriter:
+        """Optionally write intermediate values to file (compute.py:166-183)."""
+
+        def __call__(self, col_names: Iterable[str], columns: Iterable, *args, **kwargs):
+            sim.add_columns(columns, names=col_names, *args, **kwargs)
+            if write_stages:
+                sim.write(output_file, format="fits", overwrite=True)
+
+        def add_meta(self, name: str, value: Any, comment: str):
+            sim.meta[name] = (value, comment)
+            if write_stages:
+                sim.write(output_file, format="fits", overwrite=True)
+
+    sw = StagedWriter()
+    U = uniforms or {}
+
+    logv(f"Running NuSpaceSim with Energy Spectrum ({config.simulation.spectrum})")
+    logv("Computing Geometries.")
+    thrown = U["u4"] if "u4" in U else config.simulation.thrown_events
+    beta_tr, thetaArr, pathLenArr, *_ = geom(thrown, store=sw, plot=to_plot, device=True)
+    n_valid = int(beta_tr.numel())
+    logv(f"\tThrew {config.simulation.thrown_events} neutrinos. {n_valid} were valid.")
+    if n_valid == 0:
+        print("\tWARNING: No valid events thrown! Exiting early! Check geometry!")
+        return sim
+
+    torch = _lib.torch_cuda()
+    mask = geom._dev["event_mask"].bool()
+
+    def valid_u(name):
+        return _lib.to_device(U[name])[mask] if name in U else None
+
+    init_lat, init_long = geom.find_lat_long_along_traj(torch.zeros_like(beta_tr), device=True)
+    sw(("init_lat", "init_lon"), (_lib.to_host(init_lat), _lib.to_host(init_long)))
+
+    logv("Computing Energy Spectra.")
+    log_e_nu, mc_spec_norm, spec_weights_sum = spec(
+        n_valid, store=sw, plot=to_plot, device=True, u=valid_u("u_spec"))
+
+    logv("Computing Taus.")
+    tauBeta, tauLorentz, tauEnergy, showerEnergy, tauExitProb = tau(
+        beta_tr, log_e_nu, store=sw, plot=to_plot, u=valid_u("u_tau"))
+
+    logv("Computing Decay Altitudes.")
+    altDec, lenDec = eas.altDec(beta_tr, tauBeta, tauLorentz, valid_u("u_dec"), store=sw)
+
+    if config.detector.optical.enable:
+        logv("Computing EAS Optical Cherenkov light.")
+        numPEs, costhetaChEff = eas(beta_tr, altDec, showerEnergy, init_lat, init_long,
+                                    cloudf=cloud, store=sw, plot=to_plot)
+        logv("Computing Optical Monte Carlo Integral.")
+        mcint, mcintgeo, passEV, mcunc = geom.mcintegral(
+            numPEs, costhetaChEff, tauExitProb,
+            config.detector.optical.photo_electron_threshold, mc_spec_norm, spec_weights_sum,
+            lenDec=lenDec, method="Optical", store=sw)
+        sw.add_meta("OMCINT", mcint, "Optical MonteCarlo Integral")
+        sw.add_meta("OMCINTGO", mcintgeo, "Optical MonteCarlo Integral, GEO Only")
+        sw.add_meta("ONEVPASS", passEV, "Optical Number of Passing Events")
+        sw.add_meta("OMCINTUN", mcunc, "Stat unc of MonteCarlo Integral")
+        logv(f"\tMonte Carlo Integral [Optical]: {mcint}")
+        logv(f"\tMonte Carlo Integral, GEO Only [Optical]: {mcintgeo}")
+        logv(f"\tNumber of Passing Events [Optical]: {passEV}")
+        logv(f"\tStat uncert of MC Integral [Optical]: {mcunc}")
+
+    if output_file is not None and not write_stages:
+        sim.write(output_file, format="fits", overwrite=True)
+    return sim
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous block of thrown-event indices owned by ``rank``."""
+    lo = (n_total * rank) // world
+    hi = (n_total * (rank + 1)) // world
+    return lo, hi - lo
+
+
+class AcceptanceRunner:
+    """Column-free optical acceptance from in-kernel RNG (``nss_run_acceptance``)."""
+
+    def __init__(self, config, batch: int = 1 << 21, collect_stats: bool = False):
+        self.config = config
+        self.params = params_from_config(config)
+        self.taus = Taus(config)
+        self.batch = int(batch)
+        L = _lib.lib()
+        self.ws = _lib.empty(int(L.nss_acceptance_workspace_bytes(self.batch)), "uint8")
+        self.out = _lib.zeros(8)
+        self.flags = _lib.zeros(1, "int32")
+        self.stats = _lib.zeros(6, "int64") if collect_stats else None
+        self.n_kernel_launches = 0
+
+    def enqueue(self, seed: int, first_event: int, n: int):
+        """Accumulate events [first_event, first_event + n) into the device sums (async)."""
+        _lib.check(
+            _lib.lib().nss_run_acceptance(
+                C.byref(self.params), self.taus.tables, int(seed), int(first_event), int(n),
+                self.batch, _lib.ptr(self.out), _lib.ptr(self.stats), _lib.ptr(self.flags),
+                _lib.ptr(self.ws), _lib.stream_ptr()),
+            "nss_run_acceptance",
+        )
+        self.n_kernel_launches += 4 * ((int(n) + self.batch - 1) // self.batch)
+
+    def reset(self):
+        self.out.zero_()
+        self.flags.zero_()
+        if self.stats is not None:
+            self.stats.zero_()
+
+    def sums(self, all_reduce: bool = True):
+        """Device sums -> host; all-reduced over ranks when torch.distributed is up."""
+        import torch.distributed as dist
+
+        t = self.out.clone()
+        if all_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        Taus._raise_flags(self.flags)
+        return _lib.to_host(t)
+
+    def finalize(self, sums):
+        s = np.ascontiguousarray(sums, dtype=np.float64)
+        r = np.zeros(4)
+        _lib.check(
+            _lib.lib().nss_acceptance_finalize(
+                C.byref(self.params), s.ctypes.data_as(_lib.c_f64p), r.ctypes.data_as(_lib.c_f64p)),
+            "nss_acceptance_finalize",
+        )
+        return float(r[0]), float(r[1]), int(r[2]), float(r[3])
+
+
+def run_acceptance(config, n_events: int = None, seed: int = 1234, batch: int = 1 << 21):
+    """(mcintegral, mcintegralgeoonly, numEvPass, mcintegraluncert) for ``n_events`` thrown
+    events, sharded over the ranks of torch.distributed if it is initialised."""
+    import torch.distributed as dist
+
+    n_total = int(n_events if n_events is not None else config.simulation.thrown_events)
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    first, n = shard_range(n_total, rank, world)
+    r = AcceptanceRunner(config, batch=batch)
+    r.enqueue(seed, first, n)
+    return r.finalize(r.sums())

@@ -1,0 +1,120 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_tables(tid="nupyprop", ver="3"):
+    """nu2tau tables as the dict the oracle takes."""
+    from nuspacesim_b200.utils.grid import NssGrid
+
+    d = {}
+    base = os.path.join(ROOT, "nuspacesim_b200", "data", f"{tid}_tables")
+    for kind in ("pexit", "cdf"):
+        g = NssGrid.read(os.path.join(base, f"nu2tau_{kind}.{ver}.h5"))
+        d[kind] = g.data
+        for n, a in zip(g.axis_names, g.axes):
+            d[f"{kind}_{n}"] = a
+    return d
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    with np.errstate(all="ignore"):
+        r = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    r[(a == b) | (np.isnan(a) & np.isnan(b))] = 0
+    return r
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {k: np.load(os.path.join(GOLDEN, f"{k}.npz"))
+            for k in ("geometry", "taus", "altdec", "eas", "pipeline")}
+
+
+@pytest.fixture(scope="session")
+def tables_v3():
+    return load_tables()
+
+
+GEOM_TAGS = ("d525", "d33", "w10", "d1000w20")
+TAU_TABLES = dict(np3=("nupyprop", "3"), np1=("nupyprop", "1"), bdhm1=("nupyprop_bdhm", "1"),
+                  nls0=("nuleptonsim", "0"))
+PIPE_TAGS = ("c1", "e9", "e10", "d33", "e7")
+
+
+def make_config(altitude=525.0, max_ch=None, max_az=None, limb=None, loge=8.0, table=None,
+                n=None):
+    import math
+
+    from nuspacesim_b200.config import NssConfig
+
+    c = NssConfig()
+    c.detector.initial_position.altitude = float(altitude)
+    if max_ch is not None:
+        c.simulation.max_cherenkov_angle = float(max_ch)
+    if max_az is not None:
+        c.simulation.max_azimuth_angle = float(max_az)
+    if limb is not None:
+        c.simulation.angle_from_limb = float(limb)
+    c.simulation.spectrum.log_nu_energy = float(loge)
+    if table is not None:
+        c.simulation.tau_shower.id, c.simulation.tau_shower.table_version = table
+    if n is not None:
+        c.simulation.thrown_events = int(n)
+    return c
+
+
+def philox_uniforms(seed, first, n):
+    """NumPy restatement of the kernels' Philox4x32-10 streams -> (u4 (4,n), u_spec, u_tau,
+    u_dec), bit-identical to what front_kernel draws (checked against nss_philox4x32)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    W0, W1 = 0x9E3779B9, 0xBB67AE85
+    ctr = np.uint64(first) + np.arange(n, dtype=np.uint64)
+    out = []
+    for stream in (0, 1):
+        c0 = (ctr & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+        c1 = (ctr >> np.uint64(32)).astype(np.uint64)
+        c2 = np.full(n, stream, np.uint64)
+        c3 = np.zeros(n, np.uint64)
+        k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+        mask = np.uint64(0xFFFFFFFF)
+        for _ in range(10):
+            p0 = M0 * c0
+            p1 = M1 * c2
+            n0 = ((p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)) & mask
+            n1 = p1 & mask
+            n2 = ((p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)) & mask
+            n3 = p0 & mask
+            c0, c1, c2, c3 = n0, n1, n2, n3
+            k0 = (k0 + W0) & 0xFFFFFFFF
+            k1 = (k1 + W1) & 0xFFFFFFFF
+        out.append(np.stack([c0, c1, c2, c3]))
+    u = [(w.astype(np.float64) + 0.5) / 4294967296.0 for w in out]
+    return u[0], u[1][0], u[1][1], u[1][2], out

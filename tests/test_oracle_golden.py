@@ -1,0 +1,189 @@
+"""The oracle (oracle/nss_oracle.py + oracle/cphot_oracle.c) against outputs of the
+UNMODIFIED reference (tests/golden/*.npz, made by tests/golden/make_golden.py) and against
+the reference's own known-answer vectors.  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import GEOM_TAGS, PIPE_TAGS, TAU_TABLES, load_tables, rel_err
+from oracle import nss_oracle as O
+
+# Known-answer vectors copied from the reference's test data
+# (test/simulation/eas_optical/cphot_ang.py:16-66: beta = 42 deg, alt = 0..20 km,
+#  Eshow = 100 PeV, 525 km orbit, no cloud).  The reference's current code reproduces them
+#  to <= 3.0e-4, hence the tolerance.
+OLD_DPHOTS = np.array([
+    1.6210271e03, 1.8776989e03, 2.1580850e03, 2.4297334e03, 2.6037090e03, 2.5893950e03,
+    2.6665376e03, 1.9930570e03, 1.2905229e03, 7.2669135e02, 3.5919400e02, 1.5781609e02,
+    6.3526283e01, 2.4607666e01, 9.4170065e00, 3.5231948e00, 1.3178004e00, 5.0189447e-01,
+    1.9809218e-01, 8.2580306e-02, 3.6842916e-02])
+OLD_CANG = np.array([
+    1.1297, 1.0476834, 0.9589647, 0.86524945, 0.7722871, 0.68627226, 0.6104225, 0.54487425,
+    0.48861432, 0.4402858, 0.39882657, 0.3633839, 0.33331406, 0.30719605, 0.28355855,
+    0.2634559, 0.24582747, 0.22999273, 0.21532202, 0.20063952, 0.18477382])
+
+
+def _params(tagcfg):
+    alt, mch, maz, lim = tagcfg
+    return O.OracleParams(detector_altitude=alt, max_cherenkov_angle=mch, max_azimuth_angle=maz,
+                          angle_from_limb=lim)
+
+
+@pytest.mark.parametrize("tag", GEOM_TAGS)
+def test_geometry_bit_exact(golden, tag):
+    geo = golden["geometry"]
+    g = O.geom_constants(_params(geo[tag + "_cfg"]))
+    c = geo[tag + "_consts"]
+    mine = [g["earth_radius"], g["core_alt"], g["minLOSpathLen"], g["maxLOSpathLen"],
+            g["sinOfMaxThetaTrSubV"], g["maxPhiS"], g["minPhiS"], g["mcnorm"]]
+    assert np.array_equal(np.array(mine), c)
+    with np.errstate(all="ignore"):
+        t = O.geom_throw(g, geo[tag + "_u"])
+    for k, v in t.items():
+        assert np.array_equal(v, geo[f"{tag}_{k}"], equal_nan=True), k
+    for d, names in ((0.0, ("init_lat", "init_lon")), (7.5, ("lat7", "lon7"))):
+        la, lo = O.geom_lat_long(g, t, d)
+        assert np.array_equal(la, geo[f"{tag}_{names[0]}"])
+        assert np.array_equal(lo, geo[f"{tag}_{names[1]}"])
+    trig, cth, pex = geo[tag + "_mc_in"]
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(O.mcintegral(g, t, trig, cth, pex, 10.0),
+                                   geo[tag + "_mc_out"], rtol=1e-13)
+        np.testing.assert_allclose(O.mcintegral(g, t, trig, cth, pex, 10.0, 1e-6, 1e6),
+                                   geo[tag + "_mc_out_pl"], rtol=1e-13)
+
+
+def test_geometry_shape_errors():
+    g = O.geom_constants(O.OracleParams())
+    with pytest.raises(RuntimeError):
+        O.geom_throw(g, np.zeros((3, 5)))
+
+
+@pytest.mark.parametrize("tag", list(TAU_TABLES))
+def test_taus(golden, tag):
+    tg = golden["taus"]
+    T = load_tables(*TAU_TABLES[tag])
+    tb, lor, te, sh, pex = O.taus(O.OracleParams(), T, tg[tag + "_beta"], tg[tag + "_loge"],
+                                  tg[tag + "_u"])
+    assert rel_err(pex, tg[tag + "_pexit"]).max() < 1e-13
+    assert rel_err(te, tg[tag + "_tauEnergy"]).max() < 1e-13
+    assert rel_err(sh, tg[tag + "_showerEnergy"]).max() < 1e-13
+    assert rel_err(lor, tg[tag + "_tauLorentz"]).max() < 1e-13
+    assert rel_err(tb, tg[tag + "_tauBeta"]).max() < 1e-13
+
+
+def test_taus_errors(tables_v3):
+    T = tables_v3
+    with pytest.raises(ValueError):
+        O.tau_exit_prob(T["pexit"], T["pexit_log_e_nu"], T["pexit_beta_rad"], np.array([0.1]),
+                        np.array([12.5]))
+    with pytest.raises(ValueError):  # u == cdf[0]: no crossing
+        O.tau_energy(T["cdf"], T["cdf_log_e_nu"], T["cdf_beta_rad"], T["cdf_e_tau_frac"],
+                     np.array([0.1]), np.array([8.0]), np.array([0.0]))
+    assert O.cdf_sample(T["cdf"], T["cdf_log_e_nu"], T["cdf_beta_rad"], T["cdf_e_tau_frac"],
+                        np.array([]), np.array([]), np.array([])).size == 0
+
+
+def test_survey_known_answers(tables_v3):
+    """Known answers recorded from the reference in SURVEY.md 8(c)."""
+    T = tables_v3
+    p = O.OracleParams()
+    g = O.geom_constants(p)
+    u = np.array([[.1, .5, .9, .25], [.2, .4, .6, .8], [.3, .3, .3, .3], [.05, .35, .65, .95]])
+    t = O.geom_throw(g, u)
+    np.testing.assert_allclose(t["losPathLen"], [2354.714068140746, 1858.414446554829,
+                                                 1550.94979827645, 1298.220903303413], rtol=1e-12)
+    np.testing.assert_allclose(t["betaTrSubN"], [2.431471593603, 10.250049946441,
+                                                 15.643323527213, 18.149591448875], rtol=1e-11)
+    pex = O.tau_exit_prob(T["pexit"], T["pexit_log_e_nu"], T["pexit_beta_rad"],
+                          np.radians([0.05, 0.5, 1, 5.5, 20, 41.9, 43]),
+                          np.array([8, 8.1, 6, 9.33, 12, 10, 8.0]))
+    np.testing.assert_allclose(pex, [9.295e-04, 1.186998561145e-03, 1.3e-06, 1.126520859035e-03,
+                                     2.249e-05, 1.905916404001e-06, 1.192091745974e-07],
+                               rtol=2e-10)
+    z = O.cdf_sample(T["cdf"], T["cdf_log_e_nu"], T["cdf_beta_rad"], T["cdf_e_tau_frac"],
+                     np.array([8.1, 6, 9.33, 12, 10]), np.radians([0.5, 1, 5.5, 20, 41.9]),
+                     np.array([.1, .5, .9, .999, .3]))
+    np.testing.assert_allclose(z, [4.129418955339e-01, 8.369675031351e-01, 6.194613349434e-01,
+                                   3.000980635461e-04, 1.723158132956e-04], rtol=1e-11)
+    alt, ln = O.alt_dec(np.radians([1, 10, 20.0]), np.array([0.999999, 1 - 1e-10, 1 - 1e-14]),
+                        np.array([1e3, 1e6, 1e8]), 0.5)
+    np.testing.assert_allclose(ln, [6.032436589927e-05, 6.032442621766e-02, 6.032442622370],
+                               rtol=1e-11)
+    np.testing.assert_allclose(alt[1:], [1.047550335534e-02, 2.065735124765], rtol=1e-9)
+
+
+def test_altdec_bit_exact(golden):
+    a = golden["altdec"]
+    alt, ln = O.alt_dec(a["beta"], a["tauBeta"], a["tauLorentz"], a["u"])
+    assert np.array_equal(alt, a["altDec"]) and np.array_equal(ln, a["lenDec"])
+
+
+def test_engine_reference_known_answers():
+    """cphot_oracle.c against the reference's own golden vectors (cphot_ang.py:16-66)."""
+    d, c, _ = O.cphotang(np.full(21, np.radians(42.0)), np.arange(21.0), np.ones(21))
+    assert rel_err(d, OLD_DPHOTS).max() < 4e-4
+    assert rel_err(c, OLD_CANG).max() < 3e-6
+
+
+def test_engine_sweep(golden):
+    """cphot_oracle.c against CphotAng.run of today's reference on a parameter sweep."""
+    e = golden["eas"]
+    d, c, _ = O.cphotang(np.full(21, np.radians(42.0)), np.arange(21.0), np.ones(21))
+    assert rel_err(d, e["series42"][:, 0]).max() < 4e-4
+    assert rel_err(c, e["series42"][:, 1]).max() < 3e-6
+    sw = e["sweep"]
+    for det in (525.0, 33.0):
+        for top in (-np.inf, 2.0, 6.0, 12.0):
+            m = (sw[:, 0] == det) & (sw[:, 4] == top)
+            if not m.any():
+                continue
+            d, c, st = O.cphotang(sw[m, 1], sw[m, 2], sw[m, 3], det,
+                                  None if top == -np.inf else top)
+            assert np.array_equal(d == 0, sw[m, 5] == 0)  # cloud / empty early-outs
+            rd = rel_err(d, sw[m, 5])
+            assert rd.max() < 1e-3 and np.median(rd) < 1e-4
+            assert rel_err(c, sw[m, 6]).max() < 2e-6
+
+
+@pytest.mark.parametrize("tag", PIPE_TAGS)
+def test_pipeline(golden, tables_v3, tag):
+    """compute()'s optical branch stage by stage on shared uniforms."""
+    pp = golden["pipeline"]
+    alt, loge, n = pp[tag + "_cfg"]
+    p = O.OracleParams(detector_altitude=alt, log_nu_energy=loge)
+    mc, cols, t, st = O.run_path(p, tables_v3, pp[tag + "_u4"], None, pp[tag + "_u_tau"],
+                                 pp[tag + "_u_dec"], nthreads=4)
+    assert np.array_equal(t["event_mask"], pp[tag + "_event_mask"])
+    for k in ("beta_rad", "tauBeta", "tauLorentz", "tauEnergy", "showerEnergy", "tauExitProb",
+              "altDec", "lenDec"):
+        assert rel_err(cols[k], pp[f"{tag}_{k}"]).max() < 1e-13, k
+    rd = rel_err(cols["numPEs"], pp[tag + "_numPEs"])
+    assert rd.max() < 2.5e-3 and np.median(rd) < 1e-4
+    assert rel_err(cols["costhetaChEff"], pp[tag + "_costhetaChEff"]).max() < 1e-6
+    # trigger mask and pass count are exact; integrals agree to the float32 tolerance
+    assert np.array_equal(cols["numPEs"] >= 10, pp[tag + "_numPEs"] >= 10)
+    ref = pp[tag + "_mc"]
+    assert mc[2] == ref[2]
+    np.testing.assert_allclose(mc[1], ref[1], rtol=1e-13)
+    if ref[0] > 0:
+        np.testing.assert_allclose(mc[0], ref[0], rtol=1e-13)
+        np.testing.assert_allclose(mc[3], ref[3], rtol=1e-12)
+
+
+def test_oracle_against_live_reference():
+    """When /root/reference is mounted (build container), run the reference itself."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("reference tree not mounted")
+    import warnings
+
+    warnings.filterwarnings("ignore", category=DeprecationWarning)
+    ref = H.load_reference()
+    cp = ref.cphotang.CphotAng(525.0, "Greisen")
+    rng = np.random.default_rng(3)
+    b, a, e = np.radians(rng.uniform(0.5, 40, 12)), rng.uniform(0, 12, 12), 10 ** rng.uniform(-2, 1, 12)
+    want = np.array([cp.run(b[i], a[i], e[i], 0.0, 0.0, None) for i in range(12)], float)
+    d, c, _ = O.cphotang(b, a, e)
+    assert rel_err(d, want[:, 0]).max() < 1e-3
+    assert rel_err(c, want[:, 1]).max() < 2e-6
