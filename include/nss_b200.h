@@ -135,6 +135,13 @@ int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
                  const double* Eshow100PeV, int64_t n, double* dphots, double* cang,
                  unsigned long long* stats, void* stream);
 
+/* Per-launch timing of the EAS kernel with CUDA events recorded on the launching stream
+ * (for bench.py's roofline: the kernel runs inside nss_run_acceptance).  enable(1) starts
+ * recording; collect() synchronises the recorded events, returns the summed duration and
+ * the number of launches, and clears the list. */
+int nss_eas_profile_enable(int on);
+int nss_eas_profile_collect(double* total_ms, int64_t* launches);
+
 /* RegionGeom.mcintegral (region_geometry.py:364-409).  Inputs are per valid event
  * (length n_valid) unless `mask` is given, in which case they are per thrown event and
  * entries with mask == 0 are ignored.  out (device, 8 doubles):
@@ -165,6 +172,8 @@ void nss_philox4x32(uint64_t seed, uint64_t counter, uint32_t stream, uint32_t o
 
 const char* nss_strerror(int code);
 int nss_version(void);
+/* sizeof(NssParams) as compiled, so bindings can verify their struct mirror. */
+int nss_sizeof_params(void);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,8 @@ SIGNATURES = {
                         [C.c_void_p] * 6),
     "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 3 + [C.c_int64] +
                      [C.c_void_p] * 4),
+    "nss_eas_profile_enable": (C.c_int, [C.c_int]),
+    "nss_eas_profile_collect": (C.c_int, [c_f64p, c_i64p]),
     "nss_mc_workspace_bytes": (C.c_int64, []),
     "nss_mcintegral": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 7 +
                        [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double] +
@@ -108,6 +110,7 @@ SIGNATURES = {
     "nss_philox4x32": (None, [C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
     "nss_strerror": (C.c_char_p, [C.c_int]),
     "nss_version": (C.c_int, []),
+    "nss_sizeof_params": (C.c_int, []),
 }
 
 _LIB = None
@@ -131,6 +134,8 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
+        if L.nss_sizeof_params() != C.sizeof(NssParams):
+            raise NssLibraryError("NssParams mirror does not match the compiled library")
         _LIB = L
     return _LIB
 

@@ -4,6 +4,7 @@
 // Replaces: EAS.__call__ (src/nuspacesim/simulation/eas_optical/eas.py:83-138),
 //           CphotAng.__call__/run (cphotang.py:623-724), zsteps.cpp:9-45.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/nss_b200.h"
 #include "nss_eas_core.cuh"
@@ -107,6 +108,12 @@ eas_kernel(nss::EasParams P, const double* __restrict__ beta, const double* __re
 bool g_tables_ready = false;
 int g_grid_blocks[2] = {0, 0};
 
+// optional per-launch CUDA-event timing of the EAS kernel (nss_eas_profile_*)
+bool g_profile = false;
+struct ProfRec { cudaEvent_t a, b; };
+ProfRec* g_prof = nullptr;
+int g_prof_n = 0, g_prof_cap = 0;
+
 template <int MODE>
 int launch(const NssParams* p, const double* beta, const double* alt, const double* eshow,
            const uint8_t* mask, int64_t n, double* o0, double* o1, double* dph, double* cang,
@@ -140,8 +147,20 @@ int launch(const NssParams* p, const double* beta, const double* alt, const doub
   P.cloud_top = (float)p->cloud_top;
   long long need = (n + 3) / 4;  // 4 warps per block
   int blocks = (int)(need < g_grid_blocks[MODE] ? need : g_grid_blocks[MODE]);
+  ProfRec* rec = nullptr;
+  if (g_profile) {
+    if (g_prof_n == g_prof_cap) {
+      g_prof_cap = g_prof_cap ? 2 * g_prof_cap : 256;
+      g_prof = (ProfRec*)realloc(g_prof, sizeof(ProfRec) * g_prof_cap);
+    }
+    rec = &g_prof[g_prof_n++];
+    cudaEventCreate(&rec->a);
+    cudaEventCreate(&rec->b);
+    cudaEventRecord(rec->a, (cudaStream_t)stream);
+  }
   eas_kernel<MODE><<<blocks, 128, 0, (cudaStream_t)stream>>>(P, beta, alt, eshow, mask, n, o0, o1,
                                                              dph, cang, stats);
+  if (rec) cudaEventRecord(rec->b, (cudaStream_t)stream);
   return (int)cudaGetLastError();
 }
 
@@ -160,4 +179,26 @@ extern "C" int nss_cphotang(const NssParams* p, const double* betaE, const doubl
                             unsigned long long* stats, void* stream) {
   return launch<1>(p, betaE, alt, Eshow100PeV, nullptr, n, dphots, cang, nullptr, nullptr, stats,
                    stream);
+}
+
+extern "C" int nss_eas_profile_enable(int on) {
+  g_profile = on != 0;
+  return 0;
+}
+
+extern "C" int nss_eas_profile_collect(double* total_ms, int64_t* launches) {
+  double tot = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(g_prof[i].b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b);
+    cudaEventDestroy(g_prof[i].a);
+    cudaEventDestroy(g_prof[i].b);
+    if (e != cudaSuccess) { g_prof_n = 0; return (int)e; }
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = g_prof_n;
+  g_prof_n = 0;
+  return 0;
 }

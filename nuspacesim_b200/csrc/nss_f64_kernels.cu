@@ -22,7 +22,7 @@ namespace {
 constexpr double PI_D = 3.14159265358979323846;
 constexpr double F32_EPS = 1.1920928955078125e-07;
 // float32 log10 of float32 eps, as taus.py:120 evaluates it
-constexpr double LOG10_F32_EPS_F32 = -6.923689842224121;
+constexpr double LOG10_F32_EPS_F32 = -6.923690319061279;  // np.log10(np.float32 eps) as NumPy 2.3 evaluates it in float32
 constexpr double MASS_TAU = 1.77686;          // taus.py:52
 constexpr double MEAN_TAU_LIFE = 2.903e-13;   // taus.py:53
 constexpr double C_LIGHT = 299792458.0;       // astropy c (eas.py:71)
@@ -936,3 +936,5 @@ extern "C" const char* nss_strerror(int code) {
 }
 
 extern "C" int nss_version(void) { return 100; }
+
+extern "C" int nss_sizeof_params(void) { return (int)sizeof(NssParams); }

@@ -1,0 +1,310 @@
+"""Parity of the CUDA path (through the C ABI of libnss_b200.so) with the oracle and the
+reference-generated golden vectors, plus size-independent properties at large N.
+
+Tolerances (stated):
+  * float64 stages (geometry, spectrum, taus, altDec, mcintegral): rtol 1e-12; masks and
+    counts exact;
+  * float32 EAS engine: photon density / numPEs per event: median < 1e-4, 99th percentile
+    < 1e-3, max < 5e-3.  The tail is the reference's own float32 noise: CherArea uses
+    DistStep[argmax RN] (cphotang.py:653,617-621) and for showers that develop above ~35 km
+    the Greisen profile is flat over ~20 altitude steps at float32 resolution, so WHICH step
+    is the maximum is decided by rounding in np.cumsum/np.exp (one step = 1.8e-4 in area);
+    Cherenkov angle rtol 3e-5; costhetaChEff rtol 1e-6; trigger mask (numPEs >= threshold)
+    exact on every golden set.
+"""
+import numpy as np
+import pytest
+
+from conftest import (GEOM_TAGS, PIPE_TAGS, TAU_TABLES, load_tables, make_config,
+                      philox_uniforms, rel_err)
+from oracle import nss_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GEOM_ARRAYS = ("thetaTrSubV", "costhetaTrSubV", "phiTrSubV", "phiS", "losPathLen", "thetaS",
+               "costhetaNSubV", "costhetaTrSubN", "betaTrSubN", "latS", "longS", "elevAngVSubN",
+               "aziAngVSubN")
+
+
+@pytest.fixture(scope="module")
+def nss():
+    import torch
+
+    assert torch.cuda.is_available()
+    import nuspacesim_b200
+
+    return nuspacesim_b200
+
+
+def _geom_cfg(geo, tag):
+    alt, mch, maz, lim = geo[tag + "_cfg"]
+    return make_config(altitude=alt, max_ch=mch, max_az=maz, limb=lim)
+
+
+@pytest.mark.parametrize("tag", GEOM_TAGS)
+def test_geometry_vs_reference(nss, golden, tag):
+    geo = golden["geometry"]
+    g = nss.RegionGeom(_geom_cfg(geo, tag))
+    np.testing.assert_allclose(
+        [g.earth_radius, g.core_alt, g.minLOSpathLen, g.maxLOSpathLen, g.sinOfMaxThetaTrSubV,
+         g.maxPhiS, g.minPhiS, g.mcnorm], geo[tag + "_consts"], rtol=1e-14)
+    g.throw(geo[tag + "_u"])
+    want_mask = geo[tag + "_event_mask"]
+    assert np.array_equal(g.event_mask, want_mask)  # bit-exact mask
+    for k in GEOM_ARRAYS:
+        got, want = getattr(g, k), geo[f"{tag}_{k}"]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), k
+        ok = ~np.isnan(want)
+        # angles near 0 (acos(1-eps)) are compared absolutely
+        np.testing.assert_allclose(got[ok], want[ok], rtol=1e-11, atol=1e-12, err_msg=k)
+    beta, th, pl = g.beta_rad(), g.thetas(), g.pathLens()
+    assert beta.size == want_mask.sum()
+    np.testing.assert_allclose(beta, np.radians(geo[tag + "_betaTrSubN"][want_mask]), rtol=1e-11,
+                               atol=1e-14)
+    lat, lon = g.find_lat_long_along_traj(np.zeros_like(beta))
+    np.testing.assert_allclose(lat, geo[tag + "_init_lat"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(lon, geo[tag + "_init_lon"], rtol=1e-10, atol=1e-13)
+    lat, lon = g.find_lat_long_along_traj(np.full_like(beta, 7.5))
+    np.testing.assert_allclose(lat, geo[tag + "_lat7"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(lon, geo[tag + "_lon7"], rtol=1e-10, atol=1e-13)
+    trig, cth, pex = geo[tag + "_mc_in"]
+    got = g.mcintegral(trig, cth, pex, 10.0, 1.0, 1.0)
+    np.testing.assert_allclose(got, geo[tag + "_mc_out"], rtol=1e-11)
+    got = g.mcintegral(trig, cth, pex, 10.0, 1e-6, 1e6)
+    np.testing.assert_allclose(got, geo[tag + "_mc_out_pl"], rtol=1e-11)
+    assert got[2] == geo[tag + "_mc_out_pl"][2]  # pass count exact
+
+
+def test_geometry_errors_and_edges(nss):
+    g = nss.RegionGeom(make_config())
+    with pytest.raises(RuntimeError):
+        g.throw(None)
+    with pytest.raises(RuntimeError):
+        g.throw(np.zeros((3, 10)))
+    g.throw(np.zeros((4, 0)))  # empty input
+    assert g.beta_rad().size == 0
+    b, t, p = g(17)
+    assert b.size == t.size == p.size <= 17
+    # store= hook receives the reference's column names
+    seen = {}
+    g(33, store=lambda names, cols: seen.update(zip(names, cols)))
+    assert list(seen) == ["beta_rad", "theta_rad", "path_len"]
+    # Philox throw == throw(u) on the same uniforms
+    g2 = nss.RegionGeom(make_config(), seed=99)
+    g2.first_event = 12345
+    g2.throw(1000)
+    u4 = philox_uniforms(99, 12345, 1000)[0]
+    g3 = nss.RegionGeom(make_config())
+    g3.throw(u4)
+    assert np.array_equal(g2.betaTrSubN, g3.betaTrSubN)
+    assert np.array_equal(g2.event_mask, g3.event_mask)
+
+
+@pytest.mark.parametrize("tag", list(TAU_TABLES))
+def test_taus_vs_reference(nss, golden, tag):
+    tg = golden["taus"]
+    t = nss.Taus(make_config(table=TAU_TABLES[tag]))
+    beta, loge, u = tg[tag + "_beta"], tg[tag + "_loge"], tg[tag + "_u"]
+    np.testing.assert_allclose(t.tau_exit_prob(beta, loge), tg[tag + "_pexit"], rtol=1e-12)
+    np.testing.assert_allclose(t.tau_energy(beta, loge, u), tg[tag + "_tauEnergy"], rtol=1e-12)
+    tb, lor, te, sh, pex = t(beta, loge, u=u)
+    np.testing.assert_allclose(pex, tg[tag + "_pexit"], rtol=1e-12)
+    np.testing.assert_allclose(te, tg[tag + "_tauEnergy"], rtol=1e-12)
+    np.testing.assert_allclose(sh, tg[tag + "_showerEnergy"], rtol=1e-12)
+    np.testing.assert_allclose(lor, tg[tag + "_tauLorentz"], rtol=1e-12)
+    ok = ~np.isnan(tg[tag + "_tauBeta"])
+    np.testing.assert_allclose(tb[ok], tg[tag + "_tauBeta"][ok], rtol=1e-12)
+
+
+def test_taus_errors_and_sampling(nss):
+    t = nss.Taus(make_config())
+    with pytest.raises(ValueError):  # scipy bounds_error
+        t.tau_exit_prob(np.array([0.1, 0.2]), np.array([8.0, 12.5]))
+    with pytest.raises(ValueError):
+        t.tau_energy(np.array([0.1]), np.array([5.9]), np.array([0.5]))
+    with pytest.raises(ValueError):  # u == cdf[0]
+        t.tau_energy(np.array([0.1]), np.array([8.0]), np.array([0.0]))
+    with pytest.raises(RuntimeError):
+        t.tau_energy(np.array([0.1, 0.2]), np.array([8.0]), np.array([0.5, 0.5]))
+    assert t.tau_energy(np.array([]), np.array([]), np.array([])).size == 0
+    # the reference's own statistical test (test/utils/test_cdf.py:24-41): random sampling
+    n = 200000
+    rng = np.random.default_rng(5)
+    loge = rng.uniform(6, 12, n)
+    beta = np.radians(rng.uniform(1, 42, n))
+    e = t.tau_energy(beta, loge)
+    z = e / 10**loge
+    assert not np.isnan(z).any() and not np.all(z == 0) and not np.all(z == 1)
+    assert z.min() >= t.tau_cdf_grid["e_tau_frac"][0] and z.max() <= 1.0 + 1e-12
+
+
+def test_altdec_and_spectrum(nss, golden):
+    a = golden["altdec"]
+    e = nss.EAS(make_config())
+    alt, ln = e.altDec(a["beta"], a["tauBeta"], a["tauLorentz"], a["u"])
+    np.testing.assert_allclose(ln, a["lenDec"], rtol=1e-13)
+    np.testing.assert_allclose(alt, a["altDec"], rtol=1e-9, atol=1e-12)  # sqrt(...) - R cancels
+    from nuspacesim_b200.config import PowerSpectrum
+
+    c = make_config()
+    c.simulation.spectrum = PowerSpectrum(index=2.0, lower_bound=6.0, upper_bound=12.0)
+    u = np.random.default_rng(2).random(5000)
+    le, sn, sw = nss.Spectra(c)(5000, u=u)
+    p = O.OracleParams(spectrum="powerspectrum")
+    want, wsn, wsw = O.spectra(p, 5000, u)
+    np.testing.assert_allclose(le, want, rtol=1e-13)
+    assert sn == wsn and sw == wsw
+    le0, _, _ = nss.Spectra(make_config(loge=9.5))(7)
+    assert np.array_equal(le0, np.full(7, 9.5))
+
+
+def test_engine_reference_known_answers(nss):
+    """The reference's own golden vectors (test/simulation/eas_optical/cphot_ang.py:16-66)."""
+    from test_oracle_golden import OLD_CANG, OLD_DPHOTS
+
+    cp = nss.CphotAng(525.0, "Greisen")
+    z = np.zeros(21)
+    d, c = cp(np.full(21, np.radians(42.0)), np.arange(21.0), np.ones(21), z, z, None)
+    assert rel_err(d, OLD_DPHOTS).max() < 5e-4
+    assert rel_err(c, OLD_CANG).max() < 5e-6
+    assert cp([], [], [], [], [])[0].shape == ()  # empty input convention (:709-716)
+    with pytest.raises(NotImplementedError):
+        nss.CphotAng(525.0, "Gaisser-Hillas Parameterized")
+
+
+def test_engine_sweep_vs_reference_and_oracle(nss, golden):
+    sw = golden["eas"]["sweep"]
+    for det in (525.0, 33.0):
+        cp = nss.CphotAng(det, "Greisen")
+        for top in (-np.inf, 2.0, 6.0, 12.0):
+            m = (sw[:, 0] == det) & (sw[:, 4] == top)
+            if not m.any():
+                continue
+            z = np.zeros(int(m.sum()))
+            cloudf = None if top == -np.inf else (lambda *a, _t=top: np.float32(_t))
+            d, c = cp(sw[m, 1], sw[m, 2], sw[m, 3], z, z, cloudf)
+            assert np.array_equal(d == 0, sw[m, 5] == 0)  # early-outs identical
+            rr = rel_err(d, sw[m, 5])
+            assert rr.max() < 5e-3 and np.median(rr) < 1e-4, (det, top, rr.max())
+            assert np.percentile(rr, 99) < 1e-3 or rr.size < 200, (det, top)
+            assert rel_err(c, sw[m, 6]).max() < 3e-5
+            od, oc, _ = O.cphotang(sw[m, 1], sw[m, 2], sw[m, 3], det,
+                                   None if top == -np.inf else top)
+            ro = rel_err(d, od)
+            assert ro.max() < 5e-3 and np.median(ro) < 2e-5
+
+
+@pytest.mark.parametrize("tag", PIPE_TAGS)
+def test_compute_pipeline_vs_reference(nss, golden, tag):
+    """compute() on the uniforms the reference consumed: every column + acceptance."""
+    pp = golden["pipeline"]
+    alt, loge, n = pp[tag + "_cfg"]
+    cfg = make_config(altitude=alt, loge=loge, n=int(n))
+    U = dict(u4=pp[tag + "_u4"], u_tau=pp[tag + "_u_tau"], u_dec=pp[tag + "_u_dec"])
+    sim = nss.compute(cfg, uniforms=U)
+    assert sim.colnames == ["beta_rad", "theta_rad", "path_len", "init_lat", "init_lon",
+                            "log_e_nu", "tauBeta", "tauLorentz", "tauEnergy", "showerEnergy",
+                            "tauExitProb", "altDec", "lenDec", "numPEs", "costhetaChEff"]
+    assert len(sim) == int(pp[tag + "_event_mask"].sum())
+    for k in ("beta_rad", "tauBeta", "tauLorentz", "tauEnergy", "showerEnergy", "tauExitProb",
+              "lenDec", "init_lat", "init_lon"):
+        np.testing.assert_allclose(sim[k], pp[f"{tag}_{k}"], rtol=1e-10, atol=1e-13, err_msg=k)
+    np.testing.assert_allclose(sim["altDec"], pp[tag + "_altDec"], rtol=1e-8, atol=1e-12)
+    rd = rel_err(sim["numPEs"], pp[tag + "_numPEs"])
+    assert rd.max() < 5e-3 and np.percentile(rd, 99) < 1e-3 and np.median(rd) < 1e-4
+    assert rel_err(sim["costhetaChEff"], pp[tag + "_costhetaChEff"]).max() < 1e-6
+    assert np.array_equal(sim["numPEs"] >= 10, pp[tag + "_numPEs"] >= 10)  # trigger mask
+    ref = pp[tag + "_mc"]
+    assert sim.meta["ONEVPASS"][0] == ref[2]
+    np.testing.assert_allclose(sim.meta["OMCINTGO"][0], ref[1], rtol=1e-11)
+    np.testing.assert_allclose(sim.meta["OMCINT"][0], ref[0], rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(sim.meta["OMCINTUN"][0], ref[3], rtol=1e-9, atol=1e-300)
+
+
+def test_compute_writes_fits(nss, tmp_path):
+    from nuspacesim_b200 import results_table as R
+
+    cfg = make_config(n=300)
+    fn = tmp_path / "run.fits"
+    sim = nss.compute(cfg, output_file=str(fn), seed=3)
+    back = R.read_fits_table(str(fn))
+    assert back.colnames == sim.colnames and len(back) == len(sim)
+    assert np.array_equal(back["numPEs"], sim["numPEs"])
+    assert back.meta["ONEVPASS"] == sim.meta["ONEVPASS"][0]
+
+
+def test_acceptance_mode_equals_oracle_on_same_stream(nss, tables_v3):
+    """nss_run_acceptance (in-kernel Philox) vs the oracle fed the identical uniforms."""
+    cfg = make_config()
+    n, seed, first = 3000, 77, 10**10
+    r = nss.AcceptanceRunner(cfg, batch=1024, collect_stats=True)  # 3 batches, ragged tail
+    r.enqueue(seed, first, n)
+    got = r.finalize(r.sums())
+    u4, us, ut, ud, _ = philox_uniforms(seed, first, n)
+    mc, cols, t, st = O.run_path(O.OracleParams(), tables_v3, u4, us, ut, ud, nthreads=4)
+    s = r.sums()
+    assert s[4] == t["event_mask"].sum() and s[5] == n
+    assert got[2] == mc[2]  # passing events exact
+    np.testing.assert_allclose(got[1], mc[1], rtol=1e-11)
+    np.testing.assert_allclose(got[0], mc[0], rtol=1e-11)
+    np.testing.assert_allclose(got[3], mc[3], rtol=1e-6)
+    ks = r.stats.cpu().numpy()
+    assert ks[0] == st["n_raw"] * 0 + np.count_nonzero(~((cols["altDec"] < 0) | (cols["altDec"] > 20)))
+    # work counters: floor(DistStep * tan(thetaC)) flips by one on a few steps in 1e5
+    assert abs(ks[2] - st["n_val"]) <= 4 and abs(ks[3] - st["J"]) <= 1e-5 * st["J"]
+
+
+def test_acceptance_properties_at_scale(nss):
+    """Size-independent properties at 1e6 thrown events: determinism, shard invariance
+    (any split of the thrown-index range gives the same sums), MC consistency."""
+    cfg = make_config()
+    n = 1_000_000
+    r = nss.AcceptanceRunner(cfg, batch=1 << 19)
+    r.enqueue(1234, 0, n)
+    a = r.sums()
+    r.reset()
+    r.enqueue(1234, 0, n)
+    assert np.array_equal(a, r.sums())  # bit-reproducible
+    r.reset()
+    for lo, cnt in ((0, 300_001), (300_001, 199_999), (500_000, 500_000)):
+        r.enqueue(1234, lo, cnt)
+    b = r.sums()
+    assert np.array_equal(a[3:6], b[3:6])  # counts exact under re-sharding
+    np.testing.assert_allclose(a[:3], b[:3], rtol=1e-12)
+    mcint, geo, npass, unc = r.finalize(a)
+    # reference at N = 1e4: 0.1291 +- 0.0040, geo 3792.6
+    assert abs(mcint - 0.1291) < 4 * np.hypot(0.0040, unc)
+    assert abs(geo - 3792.6) / 3792.6 < 0.05
+    assert 0.98 < a[4] / n < 1.0
+    r.reset()
+    r.enqueue(4321, 0, n)  # another seed: independent estimate agrees within errors
+    m2, _, _, u2 = r.finalize(r.sums())
+    assert abs(m2 - mcint) < 5 * np.hypot(unc, u2)
+
+
+def test_mask_scan_and_compaction_ragged(nss):
+    import ctypes as C
+
+    import torch
+
+    from nuspacesim_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    for n in (1, 31, 4096, 4097, 100_003):
+        m = (rng.random(n) < 0.37).astype(np.uint8)
+        x = rng.random(n)
+        md, xd = _lib.to_device(m, "uint8"), _lib.to_device(x)
+        pos, nset = _lib.empty(n, "int64"), _lib.zeros(1, "int64")
+        ws = _lib.empty(int(L.nss_scan_workspace_bytes(n)), "uint8")
+        _lib.check(L.nss_mask_scan(_lib.ptr(md), n, _lib.ptr(pos), _lib.ptr(nset), _lib.ptr(ws),
+                                   _lib.stream_ptr()))
+        k = int(nset.item())
+        assert k == m.sum()
+        assert np.array_equal(pos.cpu().numpy(), np.cumsum(m) - m)
+        if k == 0:  # nothing to compact: a zero-length buffer has no address
+            continue
+        out = _lib.empty(k)
+        _lib.check(L.nss_compact_f64(_lib.ptr(md), _lib.ptr(pos), _lib.ptr(xd), _lib.ptr(out), n,
+                                     0, _lib.stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), x[m.astype(bool)])
