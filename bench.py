@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- thrown neutrino events per second through the whole optical path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): simulated neutrino events/sec, end-to-end optical acceptance
+(throw -> spectrum -> taus -> decay altitude -> EAS Cherenkov -> acceptance sums).
+
+Workload (SURVEY.md 8(d) config 2 = BASELINE.json configs[1]): sample_input_file.toml
+physics (525 km detector, monospectrum log10 E_nu = 8.0, theta_ch_max 3 deg, Greisen,
+nupyprop table v3, NoCloud), 1e7 thrown events per GPU per step.  Weak scaling: rank r of
+G owns thrown-event indices [step*G*n + r*n, step*G*n + (r+1)*n); the only exchange is
+one all-reduce of 8 float64 acceptance sums per step.
+
+  value  in-kernel Philox RNG, nothing but 8 doubles leaves the GPU (nss_run_acceptance).
+  e2e    the reference-facing call: nuspacesim_b200.compute(config, uniforms=...) with the
+         uniforms in pinned HOST memory (the reference draws them on the host too) and the
+         full 15-column results table + acceptance returned to the HOST, every step.
+  roofline  the EAS kernel (compute bound: FP32 pipe + MUFU); achieved =
+         algorithmic FLOPs (8(d) formula evaluated on the kernel's own work counters) /
+         CUDA-event duration of the launches inside the timed region; peak = FP32 FMA rate
+         measured on this device by nss_microbench_peaks ("of measured").
+  cpu_baseline  the oracle port (oracle/: C engine + NumPy stages) on the box's host cores,
+         bounded sample of the same workload.
+
+--impl reference times that CPU implementation alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "simulated neutrino events/sec (end-to-end optical acceptance)"
+UNIT = "events/s"
+WORKLOAD = ("sample_input_file.toml physics, monospectrum log_nu_energy=8.0, "
+            "1e7 thrown events per GPU per step, optical Cherenkov")
+NW = 28  # wavelength bins the reference really has (29 edges, cphotang.py:84-117)
+SEED = 1234
+
+
+# ------------------------------------------------------------------ helpers
+
+
+def oracle_tables():
+    from nuspacesim_b200.utils.grid import NssGrid
+
+    d = {}
+    base = os.path.join(ROOT, "nuspacesim_b200", "data", "nupyprop_tables")
+    for kind in ("pexit", "cdf"):
+        g = NssGrid.read(os.path.join(base, f"nu2tau_{kind}.3.h5"))
+        d[kind] = g.data
+        for n, a in zip(g.axis_names, g.axes):
+            d[f"{kind}_{n}"] = a
+    return d
+
+
+def time_cpu_path(n: int, cores: int, seed: int = 20240601):
+    """The oracle's restatement of compute()'s optical branch on n thrown events."""
+    from oracle import nss_oracle as O
+
+    tabs = oracle_tables()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u4, ut, ud = rng.random((4, n)), rng.random(n), rng.random(n)
+    O.build_c_oracle()
+    t0 = time.perf_counter()
+    mc, _, _, _ = O.run_path(O.OracleParams(), tabs, u4, None, ut, ud, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return dt, mc
+
+
+def cpu_baseline(target_s: float, cores: int):
+    """Calibrate on 2000 events, then time a sample sized for ~target_s seconds."""
+    dt, _ = time_cpu_path(2000, cores)
+    n = int(max(2000, min(2_000_000, 2000 * target_s / max(dt, 1e-3))))
+    dt, mc = time_cpu_path(n, cores)
+    return dict(value=n / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} thrown events of the same workload in {dt:.1f} s "
+                       f"(oracle/: C engine with OpenMP over events + NumPy stages)",
+                mcint=mc[0], mcint_unc=mc[3])
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                    power_w_max=float(max(pw)), samples=len(sm), reasons=sorted(reasons))
+
+
+def algorithmic_work(st):
+    """FLOPs and transcendentals from the kernel's work counters
+    st = {events, N_raw, N_val, J, J*N_e, n_exp, N_val*N_e, -} (sums over events)."""
+    ev, n_raw, n_val, J, JNe, n_exp, n_val_ne = (float(x) for x in st[:7])
+    flops = 45 * n_raw + (60 + 8 * NW + 25) * n_val + 25 * n_val_ne + 10 * J + 10 * JNe
+    transc = 6 * n_raw + (12 + 3 * NW + 2) * n_val + 2 * n_val_ne + 4 * J + 2 * JNe
+    return flops, transc
+
+
+# ------------------------------------------------------------------ reference arm
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = []
+    dt, _ = time_cpu_path(2000, cores)
+    n = int(max(2000, min(500_000, 2000 * 8.0 / max(dt, 1e-3))))  # ~8 s per step
+    for i in range(args.warmup + args.steps):
+        dt, mc = time_cpu_path(n, cores, seed=100 + i)
+        if i >= args.warmup:
+            per_step.append(dt)
+    tot = sum(per_step)
+    v = n * args.steps / tot
+    line = dict(
+        metric=METRIC, value=v, unit=UNIT, n_gpus=0, steps=args.steps, warmup=args.warmup,
+        ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f32 engine / f64 stages", data="synthetic", impl="reference",
+        config=dict(workload=WORKLOAD, events_per_step=n,
+                    note="the reference's own CPU algorithm for the path; /root/reference "
+                         "cannot travel to the GPU box (astropy/h5py/dask absent), so this is "
+                         "the oracle port pinned to it by tests/golden"),
+        cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
+                          sample=f"{n} thrown events per step"),
+        e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0,
+    )
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ the B200 arm
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--events", type=float, default=1e7, help="thrown events per GPU per step")
+    ap.add_argument("--batch", type=int, default=1 << 21)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 1)  # honoured as given; the contract asks for >= 3
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import nuspacesim_b200 as nss
+    from nuspacesim_b200 import _lib
+
+    L = _lib.lib()
+    cfg = nss.NssConfig()
+    n = int(args.events)
+    runner = nss.AcceptanceRunner(cfg, batch=args.batch)
+
+    def first_event(step):
+        return (step * world + rank) * n
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident acceptance mode -> `value`
+    results = []
+
+    def accept_step(step):
+        runner.reset()
+        runner.enqueue(SEED, first_event(step), n)
+        results.append(runner.sums())  # all-reduce (N > 1) + 64-byte read-back
+
+    for s in range(args.warmup):
+        accept_step(s)
+    sync_all()
+    clocks = ClockSampler(local)
+    L.nss_eas_profile_enable(1)
+    launches0 = runner.n_kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        accept_step(args.warmup + s)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    L.nss_eas_profile_enable(0)
+    eas_ms, eas_launches = C.c_double(0), C.c_int64(0)
+    _lib.check(L.nss_eas_profile_collect(C.byref(eas_ms), C.byref(eas_launches)))
+    clk = clocks.stop()
+    gpu_launches = runner.n_kernel_launches - launches0
+    value = n * world * args.steps / (ms_total * 1e-3)
+    mc = runner.finalize(results[-1])
+
+    # ---- work counters of one step's events (untimed) -> algorithmic FLOPs per launch
+    line_extra = {}
+    if rank == 0:
+        st_runner = nss.AcceptanceRunner(cfg, batch=args.batch, collect_stats=True)
+        st_runner.enqueue(SEED, first_event(args.warmup), n)
+        torch.cuda.synchronize()
+        st = st_runner.stats.cpu().numpy()
+        flops_step, transc_step = algorithmic_work(st)
+        launches_per_step = eas_launches.value / args.steps
+        eas_s_per_step = eas_ms.value * 1e-3 / args.steps
+        fp32_peak, mufu_peak = C.c_double(0), C.c_double(0)
+        _lib.check(L.nss_microbench_peaks(C.byref(fp32_peak), C.byref(mufu_peak),
+                                          _lib.stream_ptr()))
+        ach = flops_step / eas_s_per_step * 1e-12
+        line_extra["roofline"] = dict(
+            bound="fp32", kernel="eas_kernel", achieved=ach, peak=fp32_peak.value,
+            unit="TFLOP/s", frac=ach / fp32_peak.value if fp32_peak.value else None,
+            traffic=None,
+            peak_source="nss_microbench_peaks on this device (FFMA chains; MEASURED_PEAKS.json "
+                        "has no FP32 entry), of measured",
+            sfu=dict(achieved=transc_step / eas_s_per_step * 1e-12, peak=mufu_peak.value,
+                     unit="1e12 transcendentals/s (reference count) vs MUFU.EX2 issue rate",
+                     frac=(transc_step / eas_s_per_step * 1e-12) / mufu_peak.value
+                     if mufu_peak.value else None),
+            per_launch=dict(flops=flops_step / launches_per_step,
+                            transcendentals=transc_step / launches_per_step,
+                            ms=eas_ms.value / max(eas_launches.value, 1),
+                            events=float(st[0]) / launches_per_step),
+            share_of_step=eas_ms.value / ms_total,
+            work_per_eas_event=dict(N_raw=st[1] / st[0], N_val=st[2] / st[0], J=st[3] / st[0],
+                                    JNe=st[4] / st[0], exp_evaluated=st[5] / st[0]),
+            hbm_note="acceptance mode has no algorithmic DRAM traffic (0 B/event in, 64 B/step "
+                     "out); HBM peak 6535 GB/s (MEASURED_PEAKS.json) bounds only the column-mode "
+                     "stages timed in e2e",
+        )
+        del st_runner
+
+    # ---- end to end through compute() with HOST buffers -> `e2e`
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.Generator(np.random.PCG64(20240601 + rank))
+        pinned = {}
+        for name, shape in (("u4", (4, n)), ("u_tau", (n,)), ("u_dec", (n,))):
+            t = torch.empty(shape, dtype=torch.float64).pin_memory()
+            t.numpy()[...] = rng.random(shape)
+            pinned[name] = t
+        h2d = sum(t.numel() * 8 for t in pinned.values())
+        d2h = 0
+        sim = None
+        sync_all()
+        k_e2e = max(1, min(args.steps, 3))
+        for i in range(1 + k_e2e):  # one warm-up
+            if i == 1:
+                sync_all()
+                t0 = time.perf_counter()
+            sim = nss.compute(cfg, uniforms=pinned)
+            d2h = sum(np.asarray(sim[c]).nbytes for c in sim.colnames) + 4 * 8
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = dict(value=n * world * k_e2e / float(dt.item()), unit=UNIT,
+                   h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=k_e2e,
+                   api="nuspacesim_b200.compute(config, uniforms=<pinned host arrays>) -> "
+                       "15-column table + OMCINT meta on the host",
+                   mcint=float(sim.meta["OMCINT"][0]), n_valid=len(sim))
+
+    if rank == 0:
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True,
+            scaling="weak", vs_baseline=None, dtype="f32 engine / f64 stages", data="synthetic",
+            config=dict(workload=WORKLOAD, events_per_gpu_per_step=n, batch=args.batch,
+                        seed=SEED, rng="in-kernel Philox4x32-10, counter = thrown-event index",
+                        parallelism=f"event-sharded x{world}, one 8-double all-reduce per step",
+                        l2="no input arrays; per-batch stage buffers (%.0f MB) exceed the 126 MB L2"
+                           % (args.batch * 65 / 1e6)),
+            acceptance=dict(mcint=mc[0], geo=mc[1], n_pass=mc[2], unc=mc[3]),
+            clocks=clk, gpu_launches=int(gpu_launches), e2e=e2e,
+        )
+        line.update(line_extra)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
+        print(json.dumps(line, default=float))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,8 +124,10 @@ int nss_alt_dec(const double* beta, const double* tauBeta, const double* tauLore
 /* EAS.__call__ (eas.py:83-138) == CphotAng.__call__/run (cphotang.py:623-724) + zsteps.cpp
  * fused: one warp per event.  `mask` (optional, uint8) skips events with mask == 0
  * (outputs 0 / cos(1.5 deg)).  dphots/cang (optional) are CphotAng's own outputs
- * [photons/m^2, degrees].  stats (optional): 6 device uint64 work counters
- * {events, raw z-steps, retained steps, radial bins J, J*N_e, exp evaluations}. */
+ * [photons/m^2, degrees].  stats (optional): 8 device uint64 work counters
+ * {events, raw z-steps N_raw, retained steps N_val, radial bins J, J*N_e, exp evaluations
+ * in the radial x energy loop, N_val*N_e, reserved} -- the terms of SURVEY.md 8(d)'s
+ * algorithmic-work formula, accumulated over the events that ran. */
 int nss_eas_optical(const NssParams* p, const double* beta, const double* altDec,
                     const double* showerEnergy, const uint8_t* mask, int64_t n, double* numPEs,
                     double* costhetaChEff, double* dphots, double* cang,
@@ -141,6 +143,11 @@ int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
  * the number of launches, and clears the list. */
 int nss_eas_profile_enable(int on);
 int nss_eas_profile_collect(double* total_ms, int64_t* launches);
+
+/* Measured compute ceilings of the current device for the EAS kernel's roofline (SURVEY.md
+ * 8(d)): FP32 FMA rate [TFLOP/s, 2 flops per FMA] and MUFU.EX2 issue rate [1e12 op/s], each
+ * the best of 5 chains-of-8 microbenchmark launches timed with CUDA events.  Synchronises. */
+int nss_microbench_peaks(double* fp32_tflops, double* mufu_tops, void* stream);
 
 /* RegionGeom.mcintegral (region_geometry.py:364-409).  Inputs are per valid event
  * (length n_valid) unless `mask` is given, in which case they are per thrown event and

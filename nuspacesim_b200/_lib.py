@@ -99,6 +99,7 @@ SIGNATURES = {
                      [C.c_void_p] * 4),
     "nss_eas_profile_enable": (C.c_int, [C.c_int]),
     "nss_eas_profile_collect": (C.c_int, [c_f64p, c_i64p]),
+    "nss_microbench_peaks": (C.c_int, [c_f64p, c_f64p, C.c_void_p]),
     "nss_mc_workspace_bytes": (C.c_int64, []),
     "nss_mcintegral": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 7 +
                        [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double] +

@@ -21,6 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 UNITS = [
     ("nss_eas_kernel.cu", []),
     ("nss_f64_kernels.cu", ["-fmad=false"]),
+    ("nss_microbench.cu", []),
 ]
 DEPS = ["nss_eas_core.cuh", "nss_eas_tables.h", os.path.join("..", "..", "include", "nss_b200.h")]
 

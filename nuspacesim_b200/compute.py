@@ -140,7 +140,7 @@ class AcceptanceRunner:
         self.ws = _lib.empty(int(L.nss_acceptance_workspace_bytes(self.batch)), "uint8")
         self.out = _lib.zeros(8)
         self.flags = _lib.zeros(1, "int32")
-        self.stats = _lib.zeros(6, "int64") if collect_stats else None
+        self.stats = _lib.zeros(8, "int64") if collect_stats else None
         self.n_kernel_launches = 0
 
     def enqueue(self, seed: int, first_event: int, n: int):

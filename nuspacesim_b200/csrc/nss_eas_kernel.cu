@@ -74,7 +74,7 @@ eas_kernel(nss::EasParams P, const double* __restrict__ beta, const double* __re
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  nss::EasStats st = {0, 0, 0, 0, 0, 0};
+  nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long i = warp; i < n; i += nwarps) {
     const double b = beta[i], a = alt[i], e = eshow[i];
     double d = 0.0, c = (MODE == 0) ? 1.5 : 0.0;  // eas.py:106-107 defaults
@@ -102,6 +102,7 @@ eas_kernel(nss::EasParams P, const double* __restrict__ beta, const double* __re
     atomicAdd(&stats[3], st.J);
     atomicAdd(&stats[4], st.JNe);
     atomicAdd(&stats[5], st.n_exp);
+    atomicAdd(&stats[6], st.n_val_ne);
   }
 }
 

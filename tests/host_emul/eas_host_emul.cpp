@@ -36,7 +36,7 @@ extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
   P.pe_threshold = thr;
   P.has_cloud = has_cloud;
   P.cloud_top = cloud_top;
-  nss::EasStats st = {0, 0, 0, 0, 0, 0};
+  nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long i = 0; i < n; ++i) {
     double d = 0.0, c = 1.5;
     if (!(alt[i] < 0.0 || alt[i] > 20.0))
