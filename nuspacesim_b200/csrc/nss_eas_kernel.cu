@@ -1,5 +1,11 @@
-// nss_eas_kernel.cu -- sm_100a kernel for the optical-Cherenkov air-shower stage.
-// One warp per event (see nss_eas_core.cuh for the per-event algorithm).
+// nss_eas_kernel.cu -- sm_100a kernels for the optical-Cherenkov air-shower stage.
+//
+//   eas_prep_kernel    one thread per event (FP64): per-event constants + column totals
+//   eas_walk_kernel    one warp per event, persistent warps pulling events from a global
+//                      counter (showers differ 10x in length); FP32 + MUFU; no shared memory
+//   eas_finish_kernel  one thread per event (FP64): angle statistics, area, scaling, tail
+//
+// See nss_eas_core.cuh for the per-event algorithm.
 //
 // Replaces: EAS.__call__ (src/nuspacesim/simulation/eas_optical/eas.py:83-138),
 //           CphotAng.__call__/run (cphotang.py:623-724), zsteps.cpp:9-45.
@@ -27,15 +33,6 @@ struct Ops32 {
     }
     return v;
   }
-  static __device__ __forceinline__ double scan_d(double v) {
-    const int l = lane();
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      double t = __shfl_up_sync(FULL, v, d);
-      if (l >= d) v += t;
-    }
-    return v;
-  }
   static __device__ __forceinline__ double sum_d(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
@@ -45,11 +42,10 @@ struct Ops32 {
   static __device__ __forceinline__ int max_i(int v) { return __reduce_max_sync(FULL, v); }
   static __device__ __forceinline__ int min_i(int v) { return __reduce_min_sync(FULL, v); }
   static __device__ __forceinline__ bool any(bool b) { return __any_sync(FULL, b); }
-  static __device__ __forceinline__ double shift_up_d(double v, double carry) {
-    double t = __shfl_up_sync(FULL, v, 1);
-    return lane() == 0 ? carry : t;
+  static __device__ __forceinline__ float lookup11(const float*, float lane_val, int idx) {
+    return __shfl_sync(FULL, lane_val, idx);
   }
-  static __device__ __forceinline__ double last_d(double v) { return __shfl_sync(FULL, v, 31); }
+  static __device__ __forceinline__ float last_f(float v) { return __shfl_sync(FULL, v, 31); }
   // payload of the lane holding the largest key; ties -> smallest idx
   static __device__ __forceinline__ void argmax_first(float key, int idx, float payload,
                                                       float& out) {
@@ -65,35 +61,48 @@ struct Ops32 {
 };
 
 // mode 0: EAS.__call__ (altDec mask + numPEs/cos tail); mode 1: CphotAng.__call__ only.
-template <int MODE>
-__global__ void __launch_bounds__(128)
-eas_kernel(nss::EasParams P, const double* __restrict__ beta, const double* __restrict__ alt,
-           const double* __restrict__ eshow, const uint8_t* __restrict__ mask, long long n,
-           double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ dphots,
-           double* __restrict__ cang, unsigned long long* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long i = warp; i < n; i += nwarps) {
-    const double b = beta[i], a = alt[i], e = eshow[i];
-    double d = 0.0, c = (MODE == 0) ? 1.5 : 0.0;  // eas.py:106-107 defaults
+__global__ void __launch_bounds__(256)
+eas_prep_kernel(int mode, const double* __restrict__ beta, const double* __restrict__ alt,
+                const double* __restrict__ eshow, const uint8_t* __restrict__ mask, long long n,
+                nss::EasPrep* __restrict__ prep) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double a = alt[i];
     bool run = (mask == nullptr) || (mask[i] != 0);
-    if (MODE == 0) run = run && !(a < 0.0 || a > 20.0);  // eas.py:102-103
-    if (run) nss::eas_event<Ops32>(c_tables, P, b, a, e, d, c, stats ? &st : nullptr, lane == 0);
-    if (lane == 0) {
-      if (MODE == 0) {
-        double npe, cc;
-        nss::eas_tail(P, d, c, npe, cc);
-        out0[i] = npe;
-        out1[i] = cc;
-        if (dphots) dphots[i] = d;
-        if (cang) cang[i] = c;
-      } else {
-        out0[i] = d;
-        out1[i] = c;
-      }
+    if (mode == 0) run = run && !(a < 0.0 || a > 20.0);  // eas.py:102-103
+    nss::EasPrep P;
+    nss::eas_prep(c_tables, beta[i], a, eshow[i], run, P);
+    prep[i] = P;
+  }
+}
+
+constexpr int WALK_BLOCK = 128;
+
+__global__ void __launch_bounds__(WALK_BLOCK)
+eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
+                nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
+                unsigned long long* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (;;) {
+    unsigned long long i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1ull);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= (unsigned long long)n) break;
+    // first 48 bytes: scalars every lane needs; ozA[g] stays in lane g's register
+    nss::EasPrep E;
+    {
+      const float4* src = reinterpret_cast<const float4*>(prep + i);
+      float4* dst = reinterpret_cast<float4*>(&E);
+      dst[0] = __ldg(src);
+      dst[1] = __ldg(src + 1);
+      dst[2] = __ldg(src + 2);
     }
+    const float ozA_lane =
+        __ldg(reinterpret_cast<const float*>(prep + i) + 12 + (lane < 12 ? lane : 0));
+    nss::EasAcc A;
+    nss::eas_walk<Ops32>(c_tables, P, E, ozA_lane, A, stats ? &st : nullptr, lane == 0);
+    if (lane == 0) acc[i] = A;
   }
   if (stats && lane == 0 && st.n_events) {
     atomicAdd(&stats[0], st.n_events);
@@ -106,24 +115,83 @@ eas_kernel(nss::EasParams P, const double* __restrict__ beta, const double* __re
   }
 }
 
-bool g_tables_ready = false;
-int g_grid_blocks[2] = {0, 0};
+__global__ void __launch_bounds__(256)
+eas_finish_kernel(int mode, nss::EasParams P, const double* __restrict__ beta,
+                  const double* __restrict__ alt, const nss::EasAcc* __restrict__ acc,
+                  long long n, double* __restrict__ out0, double* __restrict__ out1,
+                  double* __restrict__ dphots, double* __restrict__ cang) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const nss::EasAcc A = acc[i];
+    double d = 0.0, c = 0.0;
+    nss::eas_finish(P, beta[i], alt[i], A, d, c);
+    if (mode == 0) {
+      if (A.pad == 0) c = 1.5;  // eas.py:106-107 default for events the mask skipped
+      double npe, cc;
+      nss::eas_tail(P, d, c, npe, cc);
+      out0[i] = npe;
+      out1[i] = cc;
+      if (dphots) dphots[i] = d;
+      if (cang) cang[i] = c;
+    } else {
+      out0[i] = d;
+      out1[i] = c;
+    }
+  }
+}
 
-// optional per-launch CUDA-event timing of the EAS kernel (nss_eas_profile_*)
+bool g_tables_ready = false;
+int g_walk_blocks = 0;
+
+// per-process scratch (one process per GPU): prep + acc records and the work counter
+struct Scratch {
+  nss::EasPrep* prep = nullptr;
+  nss::EasAcc* acc = nullptr;
+  unsigned long long* counter = nullptr;
+  long long cap = 0;
+  int device = -1;
+} g_scr;
+
+int scratch_reserve(long long n) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return (int)err;
+  if (g_scr.device == dev && g_scr.cap >= n) return 0;
+  if (g_scr.prep) {
+    cudaDeviceSynchronize();
+    cudaFree(g_scr.prep);
+    cudaFree(g_scr.acc);
+    cudaFree(g_scr.counter);
+    g_scr = Scratch();
+    g_tables_ready = false;
+    g_walk_blocks = 0;
+  }
+  long long cap = n < 4096 ? 4096 : n;
+  if ((err = cudaMalloc(&g_scr.prep, sizeof(nss::EasPrep) * cap)) != cudaSuccess) return (int)err;
+  if ((err = cudaMalloc(&g_scr.acc, sizeof(nss::EasAcc) * cap)) != cudaSuccess) return (int)err;
+  if ((err = cudaMalloc(&g_scr.counter, 256)) != cudaSuccess) return (int)err;
+  g_scr.cap = cap;
+  g_scr.device = dev;
+  return 0;
+}
+
+// optional per-launch CUDA-event timing of the walk kernel (nss_eas_profile_*)
 bool g_profile = false;
 struct ProfRec { cudaEvent_t a, b; };
 ProfRec* g_prof = nullptr;
 int g_prof_n = 0, g_prof_cap = 0;
 
-template <int MODE>
-int launch(const NssParams* p, const double* beta, const double* alt, const double* eshow,
-           const uint8_t* mask, int64_t n, double* o0, double* o1, double* dph, double* cang,
-           unsigned long long* stats, void* stream) {
+int launch(int mode, const NssParams* p, const double* beta, const double* alt,
+           const double* eshow, const uint8_t* mask, int64_t n, double* o0, double* o1,
+           double* dph, double* cang, unsigned long long* stats, void* stream) {
   if (!p) return NSS_E_NULL;
   if (n < 0) return NSS_E_BADARG;
   if (n == 0) return 0;
   if (!beta || !alt || !eshow || !o0 || !o1) return NSS_E_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
   cudaError_t err;
+  int rc = scratch_reserve(n);
+  if (rc != 0) return rc;
   if (!g_tables_ready) {
     nss::EasTables T;
     nss_eas_tables_init(&T);
@@ -131,13 +199,13 @@ int launch(const NssParams* p, const double* beta, const double* alt, const doub
     if (err != cudaSuccess) return (int)err;
     g_tables_ready = true;
   }
-  if (g_grid_blocks[MODE] == 0) {
+  if (g_walk_blocks == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_kernel<MODE>, 128, 0);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel, WALK_BLOCK, 0);
     if (err != cudaSuccess) return (int)err;
-    g_grid_blocks[MODE] = sms * (per_sm > 0 ? per_sm : 1);
+    g_walk_blocks = sms * (per_sm > 0 ? per_sm : 1);
   }
   nss::EasParams P;
   P.detector_altitude = p->detector_altitude;
@@ -146,8 +214,16 @@ int launch(const NssParams* p, const double* beta, const double* alt, const doub
   P.pe_threshold = p->photo_electron_threshold;
   P.has_cloud = p->has_cloud;
   P.cloud_top = (float)p->cloud_top;
-  long long need = (n + 3) / 4;  // 4 warps per block
-  int blocks = (int)(need < g_grid_blocks[MODE] ? need : g_grid_blocks[MODE]);
+
+  const int tb = 256;
+  long long g1 = (n + tb - 1) / tb;
+  if (g1 > 148LL * 64) g1 = 148LL * 64;
+  err = cudaMemsetAsync(g_scr.counter, 0, 8, s);
+  if (err != cudaSuccess) return (int)err;
+  eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, beta, alt, eshow, mask, n, g_scr.prep);
+
+  long long need = (n + (WALK_BLOCK / 32) - 1) / (WALK_BLOCK / 32);
+  int blocks = (int)(need < g_walk_blocks ? need : g_walk_blocks);
   ProfRec* rec = nullptr;
   if (g_profile) {
     if (g_prof_n == g_prof_cap) {
@@ -157,11 +233,11 @@ int launch(const NssParams* p, const double* beta, const double* alt, const doub
     rec = &g_prof[g_prof_n++];
     cudaEventCreate(&rec->a);
     cudaEventCreate(&rec->b);
-    cudaEventRecord(rec->a, (cudaStream_t)stream);
+    cudaEventRecord(rec->a, s);
   }
-  eas_kernel<MODE><<<blocks, 128, 0, (cudaStream_t)stream>>>(P, beta, alt, eshow, mask, n, o0, o1,
-                                                             dph, cang, stats);
-  if (rec) cudaEventRecord(rec->b, (cudaStream_t)stream);
+  eas_walk_kernel<<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc, g_scr.counter, stats);
+  if (rec) cudaEventRecord(rec->b, s);
+  eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, g_scr.acc, n, o0, o1, dph, cang);
   return (int)cudaGetLastError();
 }
 
@@ -171,15 +247,15 @@ extern "C" int nss_eas_optical(const NssParams* p, const double* beta, const dou
                                const double* showerEnergy, const uint8_t* mask, int64_t n,
                                double* numPEs, double* costhetaChEff, double* dphots,
                                double* cang, unsigned long long* stats, void* stream) {
-  return launch<0>(p, beta, altDec, showerEnergy, mask, n, numPEs, costhetaChEff, dphots, cang,
-                   stats, stream);
+  return launch(0, p, beta, altDec, showerEnergy, mask, n, numPEs, costhetaChEff, dphots, cang,
+                stats, stream);
 }
 
 extern "C" int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
                             const double* Eshow100PeV, int64_t n, double* dphots, double* cang,
                             unsigned long long* stats, void* stream) {
-  return launch<1>(p, betaE, alt, Eshow100PeV, nullptr, n, dphots, cang, nullptr, nullptr, stats,
-                   stream);
+  return launch(1, p, betaE, alt, Eshow100PeV, nullptr, n, dphots, cang, nullptr, nullptr, stats,
+                stream);
 }
 
 extern "C" int nss_eas_profile_enable(int on) {

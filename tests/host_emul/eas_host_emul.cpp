@@ -10,14 +10,13 @@ struct Ops1 {
   static constexpr int W = 1;
   static int lane() { return 0; }
   static float scan_f(float v) { return v; }
-  static double scan_d(double v) { return v; }
   static double sum_d(double v) { return v; }
   static int sum_i(int v) { return v; }
   static int max_i(int v) { return v; }
   static int min_i(int v) { return v; }
   static bool any(bool b) { return b; }
-  static double shift_up_d(double, double carry) { return carry; }
-  static double last_d(double v) { return v; }
+  static float lookup11(const float* tab, float, int idx) { return tab[idx]; }
+  static float last_f(float v) { return v; }
   static void argmax_first(float, int, float payload, float& out) { out = payload; }
 };
 }  // namespace
@@ -39,8 +38,13 @@ extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
   nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long i = 0; i < n; ++i) {
     double d = 0.0, c = 1.5;
-    if (!(alt[i] < 0.0 || alt[i] > 20.0))
-      nss::eas_event<Ops1>(T, P, beta[i], alt[i], eshow[i], d, c, &st, true);
+    if (!(alt[i] < 0.0 || alt[i] > 20.0)) {
+      nss::EasPrep E;
+      nss::EasAcc A;
+      nss::eas_prep(T, beta[i], alt[i], eshow[i], true, E);
+      nss::eas_walk<Ops1>(T, P, E, 0.0f, A, &st, true);
+      nss::eas_finish(P, beta[i], alt[i], A, d, c);
+    }
     double npe, cc;
     nss::eas_tail(P, d, c, npe, cc);
     numPEs[i] = npe;
@@ -52,5 +56,17 @@ extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
     stats6[0] = st.n_events; stats6[1] = st.n_raw; stats6[2] = st.n_val;
     stats6[3] = st.J; stats6[4] = st.JNe; stats6[5] = st.n_exp;
   }
+  return 0;
+}
+
+// per-event prep record, for checking the column totals against a brute-force sum
+extern "C" int nss_emul_prep(double beta, double alt, double eshow, float* out8, int* out2) {
+  nss::EasTables T;
+  nss_eas_tables_init(&T);
+  nss::EasPrep E;
+  nss::eas_prep(T, beta, alt, eshow, true, E);
+  out8[0] = E.R0; out8[1] = E.q; out8[2] = E.alt; out8[3] = E.Ldet;
+  out8[4] = E.Gtot; out8[5] = E.ozA[E.seg0]; out8[6] = E.gb; out8[7] = E.alpha;
+  out2[0] = E.n_raw; out2[1] = E.Ieang;
   return 0;
 }
