@@ -194,5 +194,61 @@ def ptr(t) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+class _HostSink:
+    """Device -> pinned host copies on a side stream (async while `deferred` is set)."""
+
+    def __init__(self):
+        torch = torch_cuda()
+        self.stream = torch.cuda.Stream()
+        self.deferred = 0
+
+    def copy(self, t) -> np.ndarray:
+        torch = torch_cuda()
+        t = t.detach()
+        if t.numel() < 4096:  # scalars / tiny arrays: the plain path is cheaper
+            return t.cpu().numpy()
+        t = t.contiguous()
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            out.copy_(t, non_blocking=True)
+        t.record_stream(self.stream)  # the caching allocator must not recycle t before the copy
+        if not self.deferred:
+            self.stream.synchronize()
+        return out.numpy()  # the array keeps the pinned tensor alive
+
+    def synchronize(self):
+        self.stream.synchronize()
+
+
+_SINK = None
+
+
+def host_sink() -> _HostSink:
+    global _SINK
+    if _SINK is None:
+        _SINK = _HostSink()
+    return _SINK
+
+
+class deferred_host_copies:
+    """Within this context `to_host` returns arrays that are filled asynchronously on a copy
+    stream (overlapping the next stage's kernels); they are complete when the context
+    exits or after `host_sink().synchronize()`."""
+
+    def __enter__(self):
+        host_sink().deferred += 1
+        return host_sink()
+
+    def __exit__(self, *exc):
+        s = host_sink()
+        s.deferred -= 1
+        s.synchronize()
+        return False
+
+
 def to_host(t) -> np.ndarray:
-    return t.detach().cpu().numpy()
+    """CUDA tensor -> NumPy array through pinned memory (fresh array owned by the caller)."""
+    return host_sink().copy(t)

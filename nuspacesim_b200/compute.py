@@ -38,6 +38,37 @@ def compute(config, verbose: bool = False, output_file: str = None, to_plot: lis
     NumPy state); ``uniforms`` may hold pre-sampled arrays ``u4`` (4, N), ``u_spec``,
     ``u_tau``, ``u_dec`` (N,) indexed by thrown event, for shared-input validation.
     """
+    with _lib.deferred_host_copies() as sink:
+        return _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms,
+                        sink)
+
+
+class StagedWriter:
+    """Optionally write intermediate values to file (compute.py:166-183).
+
+    Module-level on purpose: a class created inside compute() would keep the table (and its
+    pinned host columns) alive in a reference cycle until the next gc pass."""
+
+    def __init__(self, sim, sink, output_file, write_stages):
+        self.sim, self.sink = sim, sink
+        self.output_file, self.write_stages = output_file, write_stages
+
+    def __call__(self, col_names: Iterable[str], columns: Iterable, *args, **kwargs):
+        self.sim.add_columns(columns, names=col_names, *args, **kwargs)
+        if self.write_stages:
+            self.sink.synchronize()
+            self.sim.write(self.output_file, format="fits", overwrite=True)
+
+    def add_meta(self, name: str, value: Any, comment: str):
+        self.sim.meta[name] = (value, comment)
+        if self.write_stages:
+            self.sink.synchronize()
+            self.sim.write(self.output_file, format="fits", overwrite=True)
+
+
+def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms, sink):
+    """Body of compute(); column copies to the host are asynchronous on `sink`'s stream and
+    complete when compute() returns (or before any staged write)."""
 
     def logv(*args):
         if verbose:
@@ -52,20 +83,7 @@ def compute(config, verbose: bool = False, output_file: str = None, to_plot: lis
     if config.simulation.mode == "Target":
         raise NotImplementedError("Target (ToO) mode is outside the accelerated path")
 
-    class StagedWriter:
-        """Optionally write intermediate values to file (compute.py:166-183)."""
-
-        def __call__(self, col_names: Iterable[str], columns: Iterable, *args, **kwargs):
-            sim.add_columns(columns, names=col_names, *args, **kwargs)
-            if write_stages:
-                sim.write(output_file, format="fits", overwrite=True)
-
-        def add_meta(self, name: str, value: Any, comment: str):
-            sim.meta[name] = (value, comment)
-            if write_stages:
-                sim.write(output_file, format="fits", overwrite=True)
-
-    sw = StagedWriter()
+    sw = StagedWriter(sim, sink, output_file, write_stages)
     U = uniforms or {}
 
     logv(f"Running NuSpaceSim with Energy Spectrum ({config.simulation.spectrum})")
@@ -117,6 +135,7 @@ def compute(config, verbose: bool = False, output_file: str = None, to_plot: lis
         logv(f"\tStat uncert of MC Integral [Optical]: {mcunc}")
 
     if output_file is not None and not write_stages:
+        sink.synchronize()
         sim.write(output_file, format="fits", overwrite=True)
     return sim
 
@@ -152,7 +171,8 @@ class AcceptanceRunner:
                 _lib.ptr(self.ws), _lib.stream_ptr()),
             "nss_run_acceptance",
         )
-        self.n_kernel_launches += 4 * ((int(n) + self.batch - 1) // self.batch)
+        # per batch: front, eas_prep, eas_walk, eas_finish, accept, accept_fold
+        self.n_kernel_launches += 6 * ((int(n) + self.batch - 1) // self.batch)
 
     def reset(self):
         self.out.zero_()
