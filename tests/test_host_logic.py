@@ -273,3 +273,64 @@ def test_kernel_arithmetic_on_host_vs_oracle(emul, golden):
         assert rel_err(cc, pp[tag + "_costhetaChEff"]).max() < 1e-6
         assert np.array_equal(npe >= 10, pp[tag + "_numPEs"] >= 10)  # trigger mask exact
         assert st[0] > 0 and st[5] <= st[4]
+
+
+def test_prep_column_totals_vs_brute_force():
+    """eas_prep's whole-path totals (Gauss-Legendre grammage, closed-form ozone column) against
+    a float64 restatement of the reference's step loop (zsteps.cpp:19-32) and sums
+    (cphotang.py:376-382)."""
+    import math
+
+    src = os.path.join(ROOT, "tests", "host_emul", "eas_host_emul.cpp")
+    lib = os.path.join(ROOT, "tests", "host_emul", "libeas_host_emul.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
+                           os.path.join(ROOT, "nuspacesim_b200", "csrc"), src, "-o", lib])
+    L = ctypes.CDLL(lib)
+    f32 = np.float32
+    RADE, DL, PI = float(f32(6378.14)), float(f32(0.1)), float(f32(3.1415926))
+    OzZeta = np.array([5.35, 10.2, 14.75, 19.15, 23.55, 28.1, 32.8, 37.7, 42.85, 48.25, 100.0],
+                      f32).astype(float)
+    OzDepth = np.array([15.0, 9.0, 10.0, 31.0, 71.0, 87.2, 57.0, 29.4, 10.9, 3.2, 1.3],
+                       f32).astype(float)
+    OzDsum = np.array([310.0, 301.0, 291.0, 260.0, 189.0, 101.8, 44.8, 15.4, 4.5, 1.3, 0.1],
+                      f32).astype(float)
+
+    def totzon(z):
+        out = np.empty_like(z)
+        z0 = float(f32(5.35))
+        lo = z < z0
+        out[lo] = 310 + ((z0 - z[lo]) / z0) * 15
+        i = np.searchsorted(OzZeta, z[~lo])
+        out[~lo] = OzDsum[i] + ((OzZeta[i] - z[~lo]) / (OzZeta[i] - OzZeta[i - 1])) * OzDepth[i]
+        return out
+
+    def brute(beta, alt):
+        betaE = f32(max(beta, np.radians(1.0)))
+        tv = f32(f32(6378.14) / f32(6378.14 + 525.0)) * f32(np.cos(float(betaE)))
+        sv = float(f32(np.sin(float(f32(np.arcsin(float(tv)))))))
+        z, zs, dz = alt, [], []
+        while z <= 65.0:
+            Rad = z + RADE
+            Th = math.acos(sv * (RADE + 525.0) / Rad)
+            delz = math.sqrt(Rad * Rad + DL * DL - 2 * Rad * DL * math.cos(PI / 2 + Th)) - Rad
+            zs.append(z + delz / 2)
+            dz.append(delz)
+            z += delz
+        zs, dz = np.array(zs), np.array(dz)
+        with np.errstate(all="ignore"):
+            sq = np.sqrt(28.92 + 3.344 * zs)
+            rho = np.where(zs < 11, (1 / 0.19 / 11.861) * ((44.34 - zs) / 11.861) ** (1 / 0.19 - 1),
+                           np.where(zs < 25, (1 / 6.34) * np.exp((45.5 - zs) / 6.34),
+                                    0.5 * 3.344 / sq * np.exp(13.841 - sq)))
+        T = totzon(np.concatenate([[alt], zs]))
+        return len(zs), float(np.sum(rho * DL)), float(np.sum((T[:-1] - T[1:]) / dz * DL))
+
+    f8, i2 = (ctypes.c_float * 8)(), (ctypes.c_int * 2)()
+    cases = [(b, a) for b in (0.3, 1, 5, 20, 42) for a in (0, 5.3, 5.4, 10.9, 11.1, 20, 30, 47, 50)]
+    for b, a in cases:
+        n, G, Z = brute(np.radians(b), a)
+        L.nss_emul_prep(ctypes.c_double(np.radians(b)), ctypes.c_double(a), ctypes.c_double(1.0),
+                        f8, i2)
+        assert abs(i2[0] - n) <= 1, (b, a)
+        assert abs(f8[4] - G) / G < 1e-5, (b, a, f8[4], G)
+        assert abs(f8[5] - Z) / Z < 2e-5, (b, a, f8[5], Z)
