@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnss_b200.so")
+# NSS_B200_LIB: development override to A/B-test builds of the same library on one box
+LIB_PATH = os.environ.get("NSS_B200_LIB") or os.path.join(HERE, "libnss_b200.so")
 
 c_f64p = C.POINTER(C.c_double)
 c_u8p = C.POINTER(C.c_uint8)
