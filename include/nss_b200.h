@@ -95,6 +95,15 @@ int nss_mask_scan(const uint8_t* mask, int64_t n, int64_t* pos, int64_t* n_set, 
 int nss_compact_f64(const uint8_t* mask, const int64_t* pos, const double* in, double* out,
                     int64_t n, int to_radians, void* stream);
 
+/* Uniform `which` (0 = spectrum, 1 = tau energy, 2 = decay length, 3 = spare) of the per-event
+ * Philox stream 1 -- the words the fused nss_run_acceptance consumes -- for thrown events
+ * [first_event, first_event + n).  With mask/pos (from nss_mask_scan) only valid events are
+ * written, compacted in thrown order; with both NULL one value per thrown event.  Replaces
+ * the per-stage np.random draws (spectra.py:62, cdf.py:419-423, eas.py:67) so that compute()
+ * and the column-free mode see identical events for the same seed. */
+int nss_event_uniforms(uint64_t seed, uint64_t first_event, int64_t n, const uint8_t* mask,
+                       const int64_t* pos, int which, double* out, void* stream);
+
 /* RegionGeom.find_lat_long_along_traj (region_geometry.py:289-355) on valid events. */
 int nss_geom_lat_long(const NssParams* p, const double* thetas, const double* phis,
                       const double* elev, const double* azi, const double* longS_deg,

@@ -83,6 +83,8 @@ SIGNATURES = {
                                 C.c_void_p]),
     "nss_compact_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int, C.c_void_p]),
+    "nss_event_uniforms": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p]),
     "nss_geom_lat_long": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 7 + [C.c_int64] +
                           [C.c_void_p] * 3),
     "nss_spectrum_powerlaw": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_int64, C.c_void_p,

@@ -99,8 +99,17 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
     torch = _lib.torch_cuda()
     mask = geom._dev["event_mask"].bool()
 
+    WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2}
+
     def valid_u(name):
-        return _lib.to_device(U[name])[mask] if name in U else None
+        """Per-valid-event uniforms: the caller's array, else (when the geometry itself came
+        from Philox) the event's own counter-based stream, so that compute(seed=s) and
+        run_acceptance(seed=s) simulate identical events."""
+        if name in U:
+            return _lib.to_device(U[name])[mask]
+        if "u4" not in U:
+            return geom.event_uniforms(WHICH[name])
+        return None
 
     init_lat, init_long = geom.find_lat_long_along_traj(torch.zeros_like(beta_tr), device=True)
     sw(("init_lat", "init_lon"), (_lib.to_host(init_lat), _lib.to_host(init_long)))

@@ -277,6 +277,20 @@ compact_kernel(const uint8_t* __restrict__ mask, const int64_t* __restrict__ pos
     if (mask[i]) out[pos[i]] = (scale == 1.0) ? in[i] : in[i] * scale;
 }
 
+// uniform `which` (0 spectrum, 1 tau energy, 2 decay, 3 spare) of Philox stream 1 of every
+// valid thrown event, compacted in thrown order: the same words front_kernel consumes
+__global__ void __launch_bounds__(256)
+event_uniform_kernel(uint64_t seed, uint64_t first, int64_t n, const uint8_t* __restrict__ mask,
+                     const int64_t* __restrict__ pos, int which, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (mask && !mask[i]) continue;
+    uint32_t w[4];
+    philox4x32_10(seed, first + (uint64_t)i, 1u, w);
+    out[pos ? pos[i] : i] = u01(w[which]);
+  }
+}
+
 // ------------------------------------------------------------------ spectrum
 
 __device__ inline double powerlaw_log_e(const NssParams& p, double u) {
@@ -755,6 +769,17 @@ extern "C" int nss_compact_f64(const uint8_t* mask, const int64_t* pos, const do
   if (!mask || !pos || !in || !out) return NSS_E_NULL;
   compact_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       mask, pos, in, out, n, to_radians ? PI_D / 180.0 : 1.0);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int nss_event_uniforms(uint64_t seed, uint64_t first_event, int64_t n,
+                                  const uint8_t* mask, const int64_t* pos, int which,
+                                  double* out, void* stream) {
+  if (n < 0 || which < 0 || which > 3) return NSS_E_BADARG;
+  if (n == 0) return 0;
+  if (!out || ((mask == nullptr) != (pos == nullptr))) return NSS_E_NULL;
+  event_uniform_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(seed, first_event, n,
+                                                                          mask, pos, which, out);
   return (int)cudaGetLastError();
 }
 

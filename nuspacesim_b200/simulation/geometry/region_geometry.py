@@ -104,6 +104,20 @@ class RegionGeom:
         )
         self._n_valid = int(nset.item())
 
+    def event_uniforms(self, which: int, device: bool = True):
+        """Uniform `which` (0 spectrum, 1 tau energy, 2 decay length) of every VALID event's
+        Philox stream, in thrown order: the numbers the column-free mode draws in-kernel for
+        the same seed (extension; the reference draws from the global NumPy state)."""
+        out = _lib.empty(max(self._n_valid, 1))[: self._n_valid]
+        if self._n_valid:
+            _lib.check(
+                _lib.lib().nss_event_uniforms(
+                    self.seed, self.first_event, self._n, _lib.ptr(self._dev["event_mask"]),
+                    _lib.ptr(self._pos), int(which), _lib.ptr(out), _lib.stream_ptr()),
+                "nss_event_uniforms",
+            )
+        return out if device else _lib.to_host(out)
+
     # full-length attributes of the reference object, materialised on demand
     def __getattr__(self, name):
         dev = self.__dict__.get("_dev", {})

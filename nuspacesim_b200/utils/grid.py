@@ -106,9 +106,13 @@ class NssGrid:
 
     # ---- I/O (grid.py:314-359)
     @classmethod
-    def read(cls, filename, path: str = "/", format: str = "hdf5", **_) -> "NssGrid":
+    def read(cls, filename, path: str = "/", format: str = None, **_) -> "NssGrid":
+        if format is None:
+            format = "fits" if str(filename).lower().endswith((".fits", ".fit")) else "hdf5"
+        if format == "fits":
+            return cls._read_fits(filename)
         if format != "hdf5":
-            raise NotImplementedError("only the HDF5 NssGrid layout is implemented")
+            raise NotImplementedError(f"unknown NssGrid format {format!r}")
         f = hdf5_min.H5File(str(filename))
         g = f[path] if path not in ("/", "", None) else f
         data = np.asarray(g["__nss_grid_data__"][()])
@@ -117,13 +121,17 @@ class NssGrid:
         axes = [np.asarray(g["__nss_grid_axes__"][n][()]) for n in names]
         return cls(data, axes, names)
 
-    def write(self, filename, format: str = "hdf5", overwrite: bool = True, **_) -> None:
-        if format != "hdf5":
-            raise NotImplementedError("only the HDF5 NssGrid layout is implemented")
+    def write(self, filename, format: str = None, overwrite: bool = True, **_) -> None:
         import os
 
+        if format is None:
+            format = "fits" if str(filename).lower().endswith((".fits", ".fit")) else "hdf5"
         if os.path.exists(filename) and not overwrite:
             raise OSError(f"{filename} exists")
+        if format == "fits":
+            return self._write_fits(filename)
+        if format != "hdf5":
+            raise NotImplementedError(f"unknown NssGrid format {format!r}")
         hdf5_min.write_hdf5(
             str(filename),
             {
@@ -136,3 +144,24 @@ class NssGrid:
             },
             dict(self.meta),
         )
+
+    # ---- FITS layout (grid.py:286-311): primary image + one BinTable HDU per axis
+    @classmethod
+    def _read_fits(cls, filename) -> "NssGrid":
+        from . import fits_min
+
+        hdus = fits_min.read_hdus(filename)
+        hdr, data = hdus[0]
+        naxis = hdr["NAXIS"]
+        names = [str(hdr[f"AXIS{i}"]) for i in range(naxis)]
+        axes = [next(iter(hdus[i + 1][1].values())) for i in range(naxis)]
+        return cls(data, axes, names)
+
+    def _write_fits(self, filename) -> None:
+        from . import fits_min
+
+        with open(filename, "wb") as f:
+            f.write(fits_min.image_hdu(self._data, dict(self.meta), primary=True))
+            for axis, name in zip(self._axes, self._names):
+                f.write(fits_min.bintable_hdu({name: np.asarray(axis)},
+                                              {"AXIS": name, "EXTNAME": name}))

@@ -390,3 +390,45 @@ def test_mask_scan_and_compaction_ragged(nss):
         _lib.check(L.nss_compact_f64(_lib.ptr(md), _lib.ptr(pos), _lib.ptr(xd), _lib.ptr(out), n,
                                      0, _lib.stream_ptr()))
         assert np.array_equal(out.cpu().numpy(), x[m.astype(bool)])
+
+
+def test_cli_run_writes_results(nss, tmp_path):
+    """`python -m nuspacesim_b200 run cfg.toml N --monospectrum E -o out.fits` (apps/run.py:180)."""
+    from click.testing import CliRunner
+
+    from nuspacesim_b200 import results_table as R
+    from nuspacesim_b200.apps.cli import cli
+
+    r = CliRunner()
+    cfg, out = str(tmp_path / "c.toml"), str(tmp_path / "o.fits")
+    assert r.invoke(cli, ["create-config", cfg]).exit_code == 0
+    res = r.invoke(cli, ["run", cfg, "2e3", "--monospectrum", "9", "--monocloud", "3.0",
+                         "--seed", "11", "-o", out])
+    assert res.exit_code == 0, res.output
+    assert "Monte Carlo Integral [Optical]" in res.output
+    t = R.read_fits_table(out)
+    assert len(t.colnames) == 15 and 1900 < len(t) <= 2000
+    assert np.all(t["log_e_nu"] == 9.0)
+    acc = r.invoke(cli, ["run", cfg, "2e3", "--monospectrum", "9", "--monocloud", "3.0",
+                         "--seed", "11", "--acceptance-only"])
+    assert acc.exit_code == 0, acc.output
+    assert f"Number of Passing Events [Optical]: {int(t.meta['ONEVPASS'])}" in acc.output
+
+
+@pytest.mark.parametrize("power", [False, True])
+def test_compute_and_acceptance_mode_see_the_same_events(nss, power):
+    """compute(seed=s) (columns, stage by stage) and run_acceptance(seed=s) (fused, in-kernel
+    RNG) consume the same Philox words per thrown event: identical counts and integrals."""
+    from nuspacesim_b200.config import PowerSpectrum
+
+    cfg = make_config(n=20_000)
+    if power:
+        cfg.simulation.spectrum = PowerSpectrum(index=2.2, lower_bound=7.0, upper_bound=10.5)
+    sim = nss.compute(cfg, seed=99)
+    mcint, geo, npass, unc = nss.run_acceptance(cfg, 20_000, seed=99)
+    assert sim.meta["ONEVPASS"][0] == npass
+    np.testing.assert_allclose(sim.meta["OMCINT"][0], mcint, rtol=1e-12)
+    np.testing.assert_allclose(sim.meta["OMCINTGO"][0], geo, rtol=1e-12)
+    np.testing.assert_allclose(sim.meta["OMCINTUN"][0], unc, rtol=1e-9)
+    if power:
+        assert sim["log_e_nu"].min() >= 7.0 and sim["log_e_nu"].max() <= 10.5

@@ -334,3 +334,47 @@ def test_prep_column_totals_vs_brute_force():
         assert abs(i2[0] - n) <= 1, (b, a)
         assert abs(f8[4] - G) / G < 1e-5, (b, a, f8[4], G)
         assert abs(f8[5] - Z) / Z < 2e-5, (b, a, f8[5], Z)
+
+
+def test_nssgrid_fits_layout_roundtrip(tmp_path):
+    """NssGrid FITS layout (grid.py:286-311): primary image + one BinTable HDU per axis."""
+    from nuspacesim_b200.utils import fits_min
+    from nuspacesim_b200.utils.grid import NssGrid
+
+    g = NssGrid.read(os.path.join(ROOT, "nuspacesim_b200", "data", "nupyprop_tables",
+                                  "nu2tau_cdf.3.h5"))
+    fn = tmp_path / "cdf.fits"
+    g.write(fn)
+    back = NssGrid.read(fn)
+    assert back == g and back.axis_names == ["log_e_nu", "beta_rad", "e_tau_frac"]
+    hdus = fits_min.read_hdus(fn)
+    assert len(hdus) == 4 and hdus[0][0]["BITPIX"] == -64
+    # FITS axis order: NAXIS1 is the fastest (last NumPy) dimension
+    assert (hdus[0][0]["NAXIS1"], hdus[0][0]["NAXIS3"]) == (71, 25)
+    assert [h["AXIS"] for h, _ in hdus[1:]] == back.axis_names
+    assert os.path.getsize(fn) % 2880 == 0
+    with pytest.raises(OSError):
+        g.write(fn, overwrite=False)
+
+
+def test_cli_create_config_and_overrides(tmp_path):
+    """`create-config` writes a TOML the loader reads back; `run --help` lists the reference's
+    options (apps/run.py:58-132)."""
+    from click.testing import CliRunner
+
+    from nuspacesim_b200 import config_from_toml
+    from nuspacesim_b200.apps.cli import cli
+
+    r = CliRunner()
+    fn = str(tmp_path / "c.toml")
+    out = r.invoke(cli, ["create-config", fn, "-n", "1e4", "--powerspectrum", "2.5", "7", "11"])
+    assert out.exit_code == 0, out.output
+    c = config_from_toml(fn)
+    assert c.simulation.thrown_events == 10000
+    assert (c.simulation.spectrum.id, c.simulation.spectrum.index) == ("powerspectrum", 2.5)
+    h = r.invoke(cli, ["run", "--help"]).output
+    for opt in ("--output", "--write-stages", "--no-result-file", "--monospectrum",
+                "--powerspectrum", "--nocloud", "--monocloud", "--pressuremapcloud"):
+        assert opt in h
+    bad = r.invoke(cli, ["run", fn, "10", "--monospectrum", "8", "--powerspectrum", "2", "6", "12"])
+    assert bad.exit_code != 0
