@@ -118,3 +118,38 @@ def philox_uniforms(seed, first, n):
         out.append(np.stack([c0, c1, c2, c3]))
     u = [(w.astype(np.float64) + 0.5) / 4294967296.0 for w in out]
     return u[0], u[1][0], u[1][1], u[1][2], out
+
+
+EAS_LARGE_TAGS = ("c1", "e7", "e9", "e10", "pl10")
+
+
+@pytest.fixture(scope="session")
+def eas_large():
+    """~31 000 events of the reference's CphotAng.run (tests/golden/make_golden_eas_large.py)
+    and, per event, the oracle's own response to a 1e-5 relative change of the shower energy
+    (the conditioning of the reference)."""
+    from oracle import nss_oracle as O
+
+    G = np.load(os.path.join(GOLDEN, "eas_large.npz"))
+    out = {}
+    for tag in EAS_LARGE_TAGS:
+        b, a, e = (G[f"{tag}_{k}"] for k in ("beta_rad", "altDec", "showerEnergy"))
+        d0, c0, _ = O.cphotang(b, a, e, 525.0, None, nthreads=os.cpu_count() or 1)
+        d1, _, _ = O.cphotang(b, a, e * (1 + 1e-5), 525.0, None, nthreads=os.cpu_count() or 1)
+        out[tag] = dict(beta=b, alt=a, eshow=e, dphots=G[f"{tag}_dphots"], cang=G[f"{tag}_cang"],
+                        oracle_dphots=d0, oracle_cang=c0, sens=rel_err(d1, d0))
+    return out
+
+
+def check_engine_vs_reference(d, c, ref, what):
+    """Stated float32 tolerance of the EAS engine against the reference on a large sample:
+    median < 5e-5, 99 % < 3e-4, 99.9 % < 2e-3, every event < max(2.5e-3, 5 x conditioning);
+    Cherenkov angle rtol 5e-5."""
+    r = rel_err(d, ref["dphots"])
+    assert np.array_equal(d == 0, ref["dphots"] == 0), what
+    assert np.median(r) < 5e-5, (what, np.median(r))
+    assert np.percentile(r, 99) < 3e-4, (what, np.percentile(r, 99))
+    assert np.percentile(r, 99.9) < 2e-3, (what, np.percentile(r, 99.9))
+    bad = r > np.maximum(2.5e-3, 5 * ref["sens"])
+    assert not bad.any(), (what, np.nonzero(bad)[0][:5], r[bad][:5])
+    assert rel_err(c, ref["cang"]).max() < 5e-5, what

@@ -15,7 +15,8 @@ Tolerances (stated):
 import numpy as np
 import pytest
 
-from conftest import (GEOM_TAGS, PIPE_TAGS, TAU_TABLES, load_tables, make_config,
+from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, PIPE_TAGS, TAU_TABLES, check_engine_vs_reference,
+                      load_tables, make_config,
                       philox_uniforms, rel_err)
 from oracle import nss_oracle as O
 
@@ -432,3 +433,20 @@ def test_compute_and_acceptance_mode_see_the_same_events(nss, power):
     np.testing.assert_allclose(sim.meta["OMCINTUN"][0], unc, rtol=1e-9)
     if power:
         assert sim["log_e_nu"].min() >= 7.0 and sim["log_e_nu"].max() <= 10.5
+
+
+@pytest.mark.parametrize("tag", EAS_LARGE_TAGS)
+def test_engine_large_reference_sample(nss, eas_large, tag):
+    """CphotAng.__call__ on the GPU (nss_cphotang through the C ABI) against ~31 000 events of
+    the unmodified reference: median < 5e-5, 99 % < 3e-4, 99.9 % < 2e-3, every event below
+    max(2.5e-3, 5 x the reference's own conditioning); Cherenkov angle 5e-5."""
+    ref = eas_large[tag]
+    cp = nss.CphotAng(525.0, "Greisen")
+    d, c = cp(ref["beta"], ref["alt"], ref["eshow"], np.zeros_like(ref["beta"]),
+              np.zeros_like(ref["beta"]), None)
+    check_engine_vs_reference(np.asarray(d), np.asarray(c), ref, f"gpu/{tag}")
+    # the EAS.__call__ tail on top: trigger mask against the reference-derived numPEs
+    npe_ref = ref["dphots"] * 2.5 * 0.2
+    npe = np.asarray(d) * 2.5 * 0.2
+    near = np.abs(npe_ref / 10.0 - 1) < 2.5e-3
+    assert np.array_equal((npe >= 10.0)[~near], (npe_ref >= 10.0)[~near])

@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_tables, make_config, philox_uniforms, rel_err
+from conftest import (EAS_LARGE_TAGS, ROOT, check_engine_vs_reference, load_tables, make_config,
+                      philox_uniforms, rel_err)
 from oracle import nss_oracle as O
 
 
@@ -378,3 +379,14 @@ def test_cli_create_config_and_overrides(tmp_path):
         assert opt in h
     bad = r.invoke(cli, ["run", fn, "10", "--monospectrum", "8", "--powerspectrum", "2", "6", "12"])
     assert bad.exit_code != 0
+
+
+@pytest.mark.parametrize("tag", EAS_LARGE_TAGS)
+def test_kernel_arithmetic_on_host_vs_large_reference_sample(emul, eas_large, tag):
+    """nss_eas_core.cuh compiled for the host (W = 1) against ~31 000 events of the unmodified
+    reference: the same stated tolerance the GPU test applies."""
+    ref = eas_large[tag]
+    _, _, d, c, _ = emul(ref["beta"], ref["alt"], ref["eshow"], 525.0)
+    check_engine_vs_reference(d, c, ref, f"host-emul/{tag}")
+    ro = rel_err(d, ref["oracle_dphots"])
+    assert np.median(ro) < 5e-6  # and an order of magnitude closer to the oracle

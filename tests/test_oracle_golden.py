@@ -4,7 +4,8 @@ the reference's own known-answer vectors.  CPU only."""
 import numpy as np
 import pytest
 
-from conftest import GEOM_TAGS, PIPE_TAGS, TAU_TABLES, load_tables, rel_err
+from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, PIPE_TAGS, TAU_TABLES, check_engine_vs_reference,
+                      load_tables, rel_err)
 from oracle import nss_oracle as O
 
 # Known-answer vectors copied from the reference's test data
@@ -143,6 +144,14 @@ def test_engine_sweep(golden):
             rd = rel_err(d, sw[m, 5])
             assert rd.max() < 1e-3 and np.median(rd) < 1e-4
             assert rel_err(c, sw[m, 6]).max() < 2e-6
+
+
+@pytest.mark.parametrize("tag", EAS_LARGE_TAGS)
+def test_engine_large_reference_sample(eas_large, tag):
+    """cphot_oracle.c against ~31 000 events of the unmodified reference
+    (BASELINE.json configs 1-4 inputs)."""
+    ref = eas_large[tag]
+    check_engine_vs_reference(ref["oracle_dphots"], ref["oracle_cang"], ref, f"oracle/{tag}")
 
 
 @pytest.mark.parametrize("tag", PIPE_TAGS)
