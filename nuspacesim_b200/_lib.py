@@ -40,6 +40,8 @@ class NssParams(C.Structure):
         ("etau_frac", C.c_double),
         ("spectrum_kind", C.c_int32),
         ("has_cloud", C.c_int32),
+        ("eas_profile", C.c_int32),
+        ("reserved0", C.c_int32),
         ("log_nu_energy", C.c_double),
         ("spec_index", C.c_double),
         ("spec_lower", C.c_double),
@@ -96,10 +98,11 @@ SIGNATURES = {
     "nss_tau_sample": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
     "nss_alt_dec": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3),
-    "nss_eas_optical": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 4 + [C.c_int64] +
+    "nss_eas_optical": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 5 + [C.c_int64] +
                         [C.c_void_p] * 6),
-    "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 3 + [C.c_int64] +
+    "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 4 + [C.c_int64] +
                      [C.c_void_p] * 4),
+    "nss_eas_set_conex_table": (C.c_int, [c_f64p, C.c_int]),
     "nss_eas_profile_enable": (C.c_int, [C.c_int]),
     "nss_eas_profile_collect": (C.c_int, [c_f64p, c_i64p]),
     "nss_microbench_peaks": (C.c_int, [c_f64p, c_f64p, C.c_void_p]),

@@ -36,7 +36,8 @@ def compute(config, verbose: bool = False, output_file: str = None, to_plot: lis
 
     Extensions: ``seed`` keys the Philox streams (the reference uses the global unseeded
     NumPy state); ``uniforms`` may hold pre-sampled arrays ``u4`` (4, N), ``u_spec``,
-    ``u_tau``, ``u_dec`` (N,) indexed by thrown event, for shared-input validation.
+    ``u_tau``, ``u_dec``, ``u_profile`` (N,) indexed by thrown event, for shared-input
+    validation.
     """
     with _lib.deferred_host_copies() as sink:
         return _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms,
@@ -99,7 +100,7 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
     torch = _lib.torch_cuda()
     mask = geom._dev["event_mask"].bool()
 
-    WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2}
+    WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2, "u_profile": 3}
 
     def valid_u(name):
         """Per-valid-event uniforms: the caller's array, else (when the geometry itself came
@@ -127,8 +128,9 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
 
     if config.detector.optical.enable:
         logv("Computing EAS Optical Cherenkov light.")
+        u_prof = valid_u("u_profile") if eas.params.eas_profile == 2 else None
         numPEs, costhetaChEff = eas(beta_tr, altDec, showerEnergy, init_lat, init_long,
-                                    cloudf=cloud, store=sw, plot=to_plot)
+                                    cloudf=cloud, u_profile=u_prof, store=sw, plot=to_plot)
         logv("Computing Optical Monte Carlo Integral.")
         mcint, mcintgeo, passEV, mcunc = geom.mcintegral(
             numPEs, costhetaChEff, tauExitProb,
@@ -163,6 +165,10 @@ class AcceptanceRunner:
         self.config = config
         self.params = params_from_config(config)
         self.taus = Taus(config)
+        if self.params.eas_profile == 2:
+            from .simulation.eas_optical import cphotang
+
+            cphotang._ensure_conex_on_device()
         self.batch = int(batch)
         L = _lib.lib()
         self.ws = _lib.empty(int(L.nss_acceptance_workspace_bytes(self.batch)), "uint8")

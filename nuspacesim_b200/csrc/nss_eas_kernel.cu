@@ -61,23 +61,34 @@ struct Ops32 {
 };
 
 // mode 0: EAS.__call__ (altDec mask + numPEs/cos tail); mode 1: CphotAng.__call__ only.
+// profile 2: conex = (conex_rows, 6) float64 table, u_profile = one uniform per event picking
+// the row (replaces np.random.randint, shower_properties.py:165)
 __global__ void __launch_bounds__(256)
-eas_prep_kernel(int mode, const double* __restrict__ beta, const double* __restrict__ alt,
-                const double* __restrict__ eshow, const uint8_t* __restrict__ mask, long long n,
+eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
+                const double* __restrict__ alt, const double* __restrict__ eshow,
+                const uint8_t* __restrict__ mask, const double* __restrict__ conex,
+                int conex_rows, const double* __restrict__ u_profile, long long n,
                 nss::EasPrep* __restrict__ prep) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const double a = alt[i];
     bool run = (mask == nullptr) || (mask[i] != 0);
     if (mode == 0) run = run && !(a < 0.0 || a > 20.0);  // eas.py:102-103
+    const double* row = nullptr;
+    if (profile == 2) {
+      int r = (int)(u_profile[i] * (double)conex_rows);
+      r = r < 0 ? 0 : (r >= conex_rows ? conex_rows - 1 : r);
+      row = conex + 6 * (long long)r;
+    }
     nss::EasPrep P;
-    nss::eas_prep(c_tables, beta[i], a, eshow[i], run, P);
+    nss::eas_prep(c_tables, beta[i], a, eshow[i], run, profile, row, P);
     prep[i] = P;
   }
 }
 
 constexpr int WALK_BLOCK = 128;
 
+template <bool GH>
 __global__ void __launch_bounds__(WALK_BLOCK)
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
@@ -100,8 +111,15 @@ eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long lo
     }
     const float ozA_lane =
         __ldg(reinterpret_cast<const float*>(prep + i) + 12 + (lane < 12 ? lane : 0));
+    if (GH) {
+      const float4* src = reinterpret_cast<const float4*>(&prep[i].gh);
+      float4* dst = reinterpret_cast<float4*>(&E.gh);
+      dst[0] = __ldg(src);
+      dst[1] = __ldg(src + 1);
+      dst[2] = __ldg(src + 2);
+    }
     nss::EasAcc A;
-    nss::eas_walk<Ops32>(c_tables, P, E, ozA_lane, A, stats ? &st : nullptr, lane == 0);
+    nss::eas_walk<Ops32, GH>(c_tables, P, E, ozA_lane, A, stats ? &st : nullptr, lane == 0);
     if (lane == 0) acc[i] = A;
   }
   if (stats && lane == 0 && st.n_events) {
@@ -141,7 +159,9 @@ eas_finish_kernel(int mode, nss::EasParams P, const double* __restrict__ beta,
 }
 
 bool g_tables_ready = false;
-int g_walk_blocks = 0;
+int g_walk_blocks[2] = {0, 0};
+double* g_conex = nullptr;  // device copy of the CONEX Gaisser-Hillas table
+int g_conex_rows = 0;
 
 // per-process scratch (one process per GPU): prep + acc records and the work counter
 struct Scratch {
@@ -164,7 +184,7 @@ int scratch_reserve(long long n) {
     cudaFree(g_scr.counter);
     g_scr = Scratch();
     g_tables_ready = false;
-    g_walk_blocks = 0;
+    g_walk_blocks[0] = g_walk_blocks[1] = 0;
   }
   long long cap = n < 4096 ? 4096 : n;
   if ((err = cudaMalloc(&g_scr.prep, sizeof(nss::EasPrep) * cap)) != cudaSuccess) return (int)err;
@@ -182,12 +202,15 @@ ProfRec* g_prof = nullptr;
 int g_prof_n = 0, g_prof_cap = 0;
 
 int launch(int mode, const NssParams* p, const double* beta, const double* alt,
-           const double* eshow, const uint8_t* mask, int64_t n, double* o0, double* o1,
-           double* dph, double* cang, unsigned long long* stats, void* stream) {
+           const double* eshow, const uint8_t* mask, const double* u_profile, int64_t n,
+           double* o0, double* o1, double* dph, double* cang, unsigned long long* stats,
+           void* stream) {
   if (!p) return NSS_E_NULL;
-  if (n < 0) return NSS_E_BADARG;
+  if (n < 0 || p->eas_profile < 0 || p->eas_profile > 2) return NSS_E_BADARG;
   if (n == 0) return 0;
   if (!beta || !alt || !eshow || !o0 || !o1) return NSS_E_NULL;
+  if (p->eas_profile == 2 && (!u_profile || !g_conex)) return NSS_E_NULL;
+  const bool gh = p->eas_profile != 0;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t err;
   int rc = scratch_reserve(n);
@@ -199,13 +222,16 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     if (err != cudaSuccess) return (int)err;
     g_tables_ready = true;
   }
-  if (g_walk_blocks == 0) {
+  if (g_walk_blocks[gh] == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel, WALK_BLOCK, 0);
+    err = gh ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<true>,
+                                                             WALK_BLOCK, 0)
+             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<false>,
+                                                             WALK_BLOCK, 0);
     if (err != cudaSuccess) return (int)err;
-    g_walk_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    g_walk_blocks[gh] = sms * (per_sm > 0 ? per_sm : 1);
   }
   nss::EasParams P;
   P.detector_altitude = p->detector_altitude;
@@ -214,16 +240,19 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
   P.pe_threshold = p->photo_electron_threshold;
   P.has_cloud = p->has_cloud;
   P.cloud_top = (float)p->cloud_top;
+  P.profile = p->eas_profile;
+  P.pad = 0;
 
   const int tb = 256;
   long long g1 = (n + tb - 1) / tb;
   if (g1 > 148LL * 64) g1 = 148LL * 64;
   err = cudaMemsetAsync(g_scr.counter, 0, 8, s);
   if (err != cudaSuccess) return (int)err;
-  eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, beta, alt, eshow, mask, n, g_scr.prep);
+  eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, p->eas_profile, beta, alt, eshow, mask, g_conex,
+                                         g_conex_rows, u_profile, n, g_scr.prep);
 
   long long need = (n + (WALK_BLOCK / 32) - 1) / (WALK_BLOCK / 32);
-  int blocks = (int)(need < g_walk_blocks ? need : g_walk_blocks);
+  int blocks = (int)(need < g_walk_blocks[gh] ? need : g_walk_blocks[gh]);
   ProfRec* rec = nullptr;
   if (g_profile) {
     if (g_prof_n == g_prof_cap) {
@@ -235,7 +264,12 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     cudaEventCreate(&rec->b);
     cudaEventRecord(rec->a, s);
   }
-  eas_walk_kernel<<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc, g_scr.counter, stats);
+  if (gh)
+    eas_walk_kernel<true><<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc,
+                                                        g_scr.counter, stats);
+  else
+    eas_walk_kernel<false><<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc,
+                                                         g_scr.counter, stats);
   if (rec) cudaEventRecord(rec->b, s);
   eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, g_scr.acc, n, o0, o1, dph, cang);
   return (int)cudaGetLastError();
@@ -244,18 +278,39 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
 }  // namespace
 
 extern "C" int nss_eas_optical(const NssParams* p, const double* beta, const double* altDec,
-                               const double* showerEnergy, const uint8_t* mask, int64_t n,
-                               double* numPEs, double* costhetaChEff, double* dphots,
-                               double* cang, unsigned long long* stats, void* stream) {
-  return launch(0, p, beta, altDec, showerEnergy, mask, n, numPEs, costhetaChEff, dphots, cang,
-                stats, stream);
+                               const double* showerEnergy, const uint8_t* mask,
+                               const double* u_profile, int64_t n, double* numPEs,
+                               double* costhetaChEff, double* dphots, double* cang,
+                               unsigned long long* stats, void* stream) {
+  return launch(0, p, beta, altDec, showerEnergy, mask, u_profile, n, numPEs, costhetaChEff,
+                dphots, cang, stats, stream);
 }
 
 extern "C" int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
-                            const double* Eshow100PeV, int64_t n, double* dphots, double* cang,
-                            unsigned long long* stats, void* stream) {
-  return launch(1, p, betaE, alt, Eshow100PeV, nullptr, n, dphots, cang, nullptr, nullptr, stats,
-                stream);
+                            const double* Eshow100PeV, const double* u_profile, int64_t n,
+                            double* dphots, double* cang, unsigned long long* stats,
+                            void* stream) {
+  return launch(1, p, betaE, alt, Eshow100PeV, nullptr, u_profile, n, dphots, cang, nullptr,
+                nullptr, stats, stream);
+}
+
+extern "C" int nss_eas_set_conex_table(const double* rows_host, int nrows) {
+  if (!rows_host) return NSS_E_NULL;
+  if (nrows <= 0) return NSS_E_BADARG;
+  cudaError_t err;
+  if (g_conex) {
+    cudaDeviceSynchronize();
+    cudaFree(g_conex);
+    g_conex = nullptr;
+    g_conex_rows = 0;
+  }
+  if ((err = cudaMalloc(&g_conex, sizeof(double) * 6 * (size_t)nrows)) != cudaSuccess)
+    return (int)err;
+  err = cudaMemcpy(g_conex, rows_host, sizeof(double) * 6 * (size_t)nrows,
+                   cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return (int)err;
+  g_conex_rows = nrows;
+  return 0;
 }
 
 extern "C" int nss_eas_profile_enable(int on) {

@@ -564,6 +564,7 @@ __global__ void mc_finish(double mcnorm, double n_thrown, const double* tmp, dou
 
 struct FrontBufs {
   double *beta, *alt, *shower, *fgeo, *ctrv, *pexit, *npe, *cth;
+  double* uprof;  // CONEX row uniform (Philox stream 1, word 3): Gaisser-Hillas Fluctuated only
   uint8_t* mask;
 };
 
@@ -595,6 +596,7 @@ front_kernel(NssParams p, TabView t, uint64_t seed, uint64_t first, int64_t n, F
     b.fgeo[i] = g.costhetaTrSubN / g.costhetaNSubV / g.costhetaTrSubV;
     b.ctrv[i] = g.costhetaTrSubV;
     b.pexit[i] = to.tauExitProb;
+    if (p.eas_profile == 2) b.uprof[i] = u01(w1[3]);
   }
 }
 
@@ -892,7 +894,7 @@ extern "C" int nss_mcintegral(const NssParams* p, const double* cTrN, const doub
 
 extern "C" int64_t nss_acceptance_workspace_bytes(int64_t batch) {
   if (batch <= 0) return 0;
-  return 8 * align256(batch * 8) + align256(batch) + align256((int64_t)MC_GRID * MC_NSUM * 8);
+  return 9 * align256(batch * 8) + align256(batch) + align256((int64_t)MC_GRID * MC_NSUM * 8);
 }
 
 extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64_t seed,
@@ -904,8 +906,9 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
   cudaStream_t s = (cudaStream_t)stream;
   char* w = (char*)workspace;
   FrontBufs b;
-  double** slots[8] = {&b.beta, &b.alt, &b.shower, &b.fgeo, &b.ctrv, &b.pexit, &b.npe, &b.cth};
-  for (int k = 0; k < 8; ++k) {
+  double** slots[9] = {&b.beta, &b.alt,   &b.shower, &b.fgeo, &b.ctrv,
+                       &b.pexit, &b.npe, &b.cth,    &b.uprof};
+  for (int k = 0; k < 9; ++k) {
     *slots[k] = (double*)w;
     w += align256(batch * 8);
   }
@@ -919,7 +922,8 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
     const int64_t m = (n - off) < batch ? (n - off) : batch;
     front_kernel<<<grid_for(m, 256), 256, 0, s>>>(*p, tv, seed, first_event + (uint64_t)off, m, b,
                                                   flags);
-    int rc = nss_eas_optical(p, b.beta, b.alt, b.shower, b.mask, m, b.npe, b.cth, nullptr,
+    int rc = nss_eas_optical(p, b.beta, b.alt, b.shower, b.mask,
+                             p->eas_profile == 2 ? b.uprof : nullptr, m, b.npe, b.cth, nullptr,
                              nullptr, stats, stream);
     if (rc != 0) return rc;
     int grid = (int)((m + MC_BLOCK - 1) / MC_BLOCK < MC_GRID ? (m + MC_BLOCK - 1) / MC_BLOCK

@@ -35,6 +35,9 @@ def params_from_config(config) -> _lib.NssParams:
         p.spectrum_kind = 0
         p.log_nu_energy = float(spec.log_nu_energy)
         p.spec_index, p.spec_lower, p.spec_upper = 2.0, 6.0, 12.0
+    prof = getattr(sim, "eas_long_profile", "Greisen")
+    p.eas_profile = {"Default": 0, "Greisen": 0, "Gaisser-Hillas Parameterized": 1,
+                     "Gaisser-Hillas Fluctuated": 2}[prof]
     cloud = getattr(sim, "cloud_model", None)
     cid = getattr(cloud, "id", "no_cloud")
     if cid == "monocloud":

@@ -8,12 +8,37 @@ the pybind11 ``zsteps``) is the fused warp-per-event kernel ``nss_cphotang``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from ... import _lib
 
-__all__ = ["CphotAng"]
+__all__ = ["CphotAng", "PROFILES", "conex_table"]
+
+#: simulation.eas_long_profile -> NssParams.eas_profile (cphotang.py:256-276)
+PROFILES = {"Greisen": 0, "Gaisser-Hillas Parameterized": 1, "Gaisser-Hillas Fluctuated": 2}
+
+_CONEX = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                      "data", "CONEX_table", "gh_conex_pi_E17_95deg_0km_eposlhc.npy")
+_conex_uploaded = None
+
+
+def conex_table():
+    """(1000, 6) float64 rows Nm, Xm, X0, p1, p2, p3: columns 4..9 of the CONEX fit table the
+    reference loads with np.loadtxt(usecols=(4..9)) (cphotang.py:266-276)."""
+    return np.load(_CONEX)
+
+
+def _ensure_conex_on_device():
+    """Upload the CONEX table once per process (and again after a device change)."""
+    global _conex_uploaded
+    dev = _lib.torch_cuda().cuda.current_device()
+    if _conex_uploaded != dev:
+        t = np.ascontiguousarray(conex_table(), dtype=np.float64)
+        _lib.check(_lib.lib().nss_eas_set_conex_table(t.ctypes.data_as(_lib.c_f64p), t.shape[0]),
+                   "nss_eas_set_conex_table")
+        _conex_uploaded = dev
 
 
 def cloud_scalar(cloudf):
@@ -27,12 +52,12 @@ def cloud_scalar(cloudf):
 
 
 class CphotAng:
-    def __init__(self, detector_altitude, longitudinal_profile_func="Greisen"):
-        if longitudinal_profile_func != "Greisen":
-            raise NotImplementedError(
-                "only the Greisen longitudinal profile is on the accelerated path "
-                "(Gaisser-Hillas variants: SURVEY.md 8(f) rank 4)"
-            )
+    def __init__(self, detector_altitude, longitudinal_profile_func="Greisen", seed: int = 0):
+        if longitudinal_profile_func not in PROFILES:
+            # the reference leaves particle_count undefined here and fails on first use
+            raise ValueError(f"unknown longitudinal profile {longitudinal_profile_func!r}")
+        self.longitudinal_profile_func = longitudinal_profile_func
+        self._rng = np.random.Generator(np.random.Philox(key=int(seed) + 3))
         self.detector_altitude = detector_altitude
         self.dtype = np.float32
         self.params = _lib.NssParams()
@@ -40,8 +65,24 @@ class CphotAng:
         self.params.telescope_effective_area = 1.0
         self.params.quantum_efficiency = 1.0
         self.params.photo_electron_threshold = 1.0
+        self.params.eas_profile = PROFILES[longitudinal_profile_func]
 
-    def __call__(self, betaE, alt, Eshow100PeV, init_lat, init_long, cloudf=None, stats=None):
+    def profile_uniforms(self, n, u_profile=None):
+        """Device array of the per-event uniforms that pick the CONEX row (row = floor(u *
+        nrows); the reference calls np.random.randint per event, shower_properties.py:165),
+        or None for the profiles that draw nothing."""
+        if self.params.eas_profile != 2:
+            return None
+        _ensure_conex_on_device()
+        if u_profile is None:
+            u_profile = self._rng.random(n)
+        up = _lib.to_device(u_profile)
+        if up.numel() != n:
+            raise RuntimeError("u_profile must hold one uniform per event")
+        return up
+
+    def __call__(self, betaE, alt, Eshow100PeV, init_lat, init_long, cloudf=None, stats=None,
+                 u_profile=None):
         """-> (Dphots [photons/m^2], Cang [deg]) per event (cphotang.py:703-724)."""
         if (len(betaE) < 1 or len(alt) < 1 or len(Eshow100PeV) < 1 or len(init_lat) < 1
                 or len(init_long) < 1):
@@ -51,15 +92,18 @@ class CphotAng:
         n = b.numel()
         self.params.has_cloud, self.params.cloud_top = cloud_scalar(cloudf)
         d, c = _lib.empty(n), _lib.empty(n)
+        up = self.profile_uniforms(n, u_profile)
         _lib.check(
-            _lib.lib().nss_cphotang(C.byref(self.params), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e), n,
-                                    _lib.ptr(d), _lib.ptr(c), _lib.ptr(stats), _lib.stream_ptr()),
+            _lib.lib().nss_cphotang(C.byref(self.params), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e),
+                                    _lib.ptr(up), n, _lib.ptr(d), _lib.ptr(c), _lib.ptr(stats),
+                                    _lib.stream_ptr()),
             "nss_cphotang",
         )
         return (d, c) if dev else (_lib.to_host(d), _lib.to_host(c))
 
-    def run(self, betaE, alt, Eshow100PeV, lat, long, cloudf=None):
+    def run(self, betaE, alt, Eshow100PeV, lat, long, cloudf=None, u_profile=None):
         """One event (cphotang.py:623-701)."""
         d, c = self(np.array([betaE], float), np.array([alt], float),
-                    np.array([Eshow100PeV], float), [lat], [long], cloudf)
+                    np.array([Eshow100PeV], float), [lat], [long], cloudf,
+                    u_profile=None if u_profile is None else np.array([u_profile], float))
         return np.float32(d[0]), np.float32(c[0])

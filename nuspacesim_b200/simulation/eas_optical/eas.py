@@ -26,7 +26,8 @@ class EAS:
         self.config = config
         self.params = params_from_config(config)
         self.CphotAng = CphotAng(
-            config.detector.initial_position.altitude, config.simulation.eas_long_profile
+            config.detector.initial_position.altitude, config.simulation.eas_long_profile,
+            seed=seed,
         )
         self._rng = np.random.Generator(np.random.Philox(key=int(seed) + 2))
         #: optional device uint64[6] work counters filled by the kernel
@@ -52,17 +53,21 @@ class EAS:
     @decorators.nss_result_plot()
     @decorators.nss_result_store("numPEs", "costhetaChEff")
     def __call__(self, beta, altDec, showerEnergy, init_lat, init_long, *args, cloudf=None,
-                 **kwargs):
-        """Electromagnetic Air Shower operation (eas.py:83-138) -> (numPEs, costhetaChEff)."""
+                 u_profile=None, **kwargs):
+        """Electromagnetic Air Shower operation (eas.py:83-138) -> (numPEs, costhetaChEff).
+
+        ``u_profile`` (extension, "Gaisser-Hillas Fluctuated" only): one uniform per event
+        selecting the CONEX row; drawn from the seeded generator when omitted."""
         dev = any(_lib.is_device_array(x) for x in (beta, altDec, showerEnergy))
         b, a, e = _lib.to_device(beta), _lib.to_device(altDec), _lib.to_device(showerEnergy)
         n = b.numel()
         p = self.params
         p.has_cloud, p.cloud_top = cloud_scalar(cloudf)
         npe, cth = _lib.empty(n), _lib.empty(n)
+        up = self.CphotAng.profile_uniforms(n, u_profile)
         _lib.check(
-            _lib.lib().nss_eas_optical(C.byref(p), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e), None, n,
-                                       _lib.ptr(npe), _lib.ptr(cth), None, None,
+            _lib.lib().nss_eas_optical(C.byref(p), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e), None,
+                                       _lib.ptr(up), n, _lib.ptr(npe), _lib.ptr(cth), None, None,
                                        _lib.ptr(self.stats), _lib.stream_ptr()),
             "nss_eas_optical",
         )

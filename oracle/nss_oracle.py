@@ -72,6 +72,7 @@ class OracleParams:
     spec_lower: float = 6.0
     spec_upper: float = 12.0
     cloud_top: Optional[float] = None  # None == NoCloud (cloudf is constant 0 -> see eas())
+    eas_long_profile: str = "Greisen"  # config.simulation.eas_long_profile
 
 
 # --------------------------------------------------------------------------- geometry
@@ -423,8 +424,26 @@ def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nthreads=1):
-    """CphotAng.__call__ (cphotang.py:703-724) -> (dphots, cang_deg, stats)."""
+PROFILES = {"Greisen": 0, "Gaisser-Hillas Parameterized": 1, "Gaisser-Hillas Fluctuated": 2}
+
+
+def _profile_args(profile, gh_rows, n):
+    kind = PROFILES[profile]
+    if kind == 2:
+        rows = np.ascontiguousarray(gh_rows, dtype=np.float64)
+        if rows.shape != (n, 6):
+            raise ValueError("gh_rows must be (n, 6): Nm, Xm, X0, p1, p2, p3 per event")
+        return ctypes.c_int(kind), _dp(rows), rows
+    return ctypes.c_int(kind), None, None
+
+
+def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nthreads=1,
+             profile="Greisen", gh_rows=None):
+    """CphotAng.__call__ (cphotang.py:703-724) -> (dphots, cang_deg, stats).
+
+    ``profile`` is the reference's ``longitudinal_profile_func``; for "Gaisser-Hillas
+    Fluctuated" ``gh_rows[i]`` is the CONEX row (columns 4..9) the reference would draw for
+    event i with ``np.random.randint`` (shower_properties.py:165-166)."""
     beta = np.ascontiguousarray(beta, dtype=np.float64)
     alt = np.ascontiguousarray(alt, dtype=np.float64)
     es = np.ascontiguousarray(eshow100pev, dtype=np.float64)
@@ -432,16 +451,17 @@ def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nt
     d, c = np.zeros(n), np.zeros(n)
     st = _Stats()
     t = _ctables()
-    _lib().nss_oracle_cphotang(
+    kind, rows_p, _keep = _profile_args(profile, gh_rows, n)
+    _lib().nss_oracle_cphotang_profile(
         ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es),
         ctypes.c_int(cloud_top is not None),
         ctypes.c_float(0.0 if cloud_top is None else cloud_top),
         ctypes.c_double(detector_altitude), _dp(d), _dp(c), ctypes.byref(st),
-        ctypes.c_int(nthreads))
+        ctypes.c_int(nthreads), kind, rows_p)
     return d, c, {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 
-def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1):
+def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1, gh_rows=None):
     """EAS.__call__ (eas.py:83-138) -> (numPEs, costhetaChEff, dphots, cang_deg, stats)."""
     beta = np.ascontiguousarray(beta, dtype=np.float64)
     alt = np.ascontiguousarray(altDec, dtype=np.float64)
@@ -450,21 +470,28 @@ def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1):
     npe, cth, d, c = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
     st = _Stats()
     t = _ctables()
-    _lib().nss_oracle_eas(
+    kind, rows_p, _keep = _profile_args(getattr(p, "eas_long_profile", "Greisen"), gh_rows, n)
+    _lib().nss_oracle_eas_profile(
         ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es),
         ctypes.c_int(p.cloud_top is not None),
         ctypes.c_float(0.0 if p.cloud_top is None else p.cloud_top),
         ctypes.c_double(p.detector_altitude), ctypes.c_double(p.telescope_effective_area),
         ctypes.c_double(p.quantum_efficiency), ctypes.c_double(p.photo_electron_threshold),
-        _dp(npe), _dp(cth), _dp(d), _dp(c), ctypes.byref(st), ctypes.c_int(nthreads))
+        _dp(npe), _dp(cth), _dp(d), _dp(c), ctypes.byref(st), ctypes.c_int(nthreads), kind,
+        rows_p)
     return npe, cth, d, c, {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 
 # --------------------------------------------------------------------------- whole path
 
 
-def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1):
+def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1, u_profile=None,
+             conex=None):
     """compute.py:186-257 (optical branch) on pre-sampled uniforms.
+
+    For "Gaisser-Hillas Fluctuated", ``u_profile`` (length N, by thrown event) picks the row
+    of ``conex`` ((nrows, 6) float64) as floor(u * nrows) where the reference calls
+    np.random.randint(0, nrows) (shower_properties.py:165).
 
     ``u4`` is (4, N); ``u_spec``, ``u_tau``, ``u_dec`` are length-N arrays indexed
     by THROWN event (event i uses element i whether or not it is valid), which is
@@ -477,7 +504,13 @@ def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1):
     le, sn, sw = spectra(p, int(m.sum()), None if u_spec is None else np.asarray(u_spec)[m])
     tb, lor, te, sh, pex = taus(p, tables, beta, le, np.asarray(u_tau)[m])
     alt, length = alt_dec(beta, tb, lor, np.asarray(u_dec)[m])
-    npe, cth, d, c, st = eas(p, beta, alt, sh, nthreads=nthreads)
+    rows = None
+    if PROFILES[getattr(p, "eas_long_profile", "Greisen")] == 2:
+        conex = np.asarray(conex, dtype=np.float64)
+        idx = np.minimum((np.asarray(u_profile)[m] * conex.shape[0]).astype(np.int64),
+                         conex.shape[0] - 1)
+        rows = conex[idx]
+    npe, cth, d, c, st = eas(p, beta, alt, sh, nthreads=nthreads, gh_rows=rows)
     mc = mcintegral(g, t, npe, cth, pex, p.photo_electron_threshold, sn, sw)
     cols = dict(beta_rad=beta, theta_rad=t["thetaTrSubV"][m], path_len=t["losPathLen"][m],
                 log_e_nu=le, tauBeta=tb, tauLorentz=lor, tauEnergy=te, showerEnergy=sh,

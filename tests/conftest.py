@@ -141,13 +141,51 @@ def eas_large():
     return out
 
 
-def check_engine_vs_reference(d, c, ref, what):
+GH_TAGS = ("c1", "e10", "pl10")
+GH_PROFILES = {"ghp": "Gaisser-Hillas Parameterized", "ghf": "Gaisser-Hillas Fluctuated"}
+
+
+def conex_rows():
+    """(1000, 6) CONEX Gaisser-Hillas fit rows shipped with the package (imported from the
+    reference's data file by tools/import_tables.py)."""
+    return np.load(os.path.join(ROOT, "nuspacesim_b200", "data", "CONEX_table",
+                                "gh_conex_pi_E17_95deg_0km_eposlhc.npy"))
+
+
+@pytest.fixture(scope="session")
+def eas_gh():
+    """7 000 events of the reference's CphotAng.run with the two Gaisser-Hillas profiles
+    (tests/golden/make_golden_gh.py; the CONEX row each fluctuated event drew is recorded),
+    plus the oracle's conditioning per event as in `eas_large`."""
+    from oracle import nss_oracle as O
+
+    G = np.load(os.path.join(GOLDEN, "eas_gh.npz"))
+    T = conex_rows()
+    nt = os.cpu_count() or 1
+    out = {}
+    for tag in GH_TAGS:
+        b, a, e = (G[f"{tag}_{k}"] for k in ("beta_rad", "altDec", "showerEnergy"))
+        idx = G[f"{tag}_row"]
+        for short, prof in GH_PROFILES.items():
+            kw = dict(profile=prof, gh_rows=T[idx], nthreads=nt)
+            d0, c0, _ = O.cphotang(b, a, e, 525.0, None, **kw)
+            d1, _, _ = O.cphotang(b, a, e * (1 + 1e-5), 525.0, None, **kw)
+            out[tag, short] = dict(beta=b, alt=a, eshow=e, row=idx, rows=T[idx],
+                                   u_profile=(idx + 0.5) / T.shape[0],
+                                   dphots=G[f"{tag}_{short}_dphots"],
+                                   cang=G[f"{tag}_{short}_cang"], oracle_dphots=d0,
+                                   oracle_cang=c0, sens=rel_err(d1, d0))
+    return out
+
+
+def check_engine_vs_reference(d, c, ref, what, median_tol=5e-5):
     """Stated float32 tolerance of the EAS engine against the reference on a large sample:
     median < 5e-5, 99 % < 3e-4, 99.9 % < 2e-3, every event < max(2.5e-3, 5 x conditioning);
-    Cherenkov angle rtol 5e-5."""
+    Cherenkov angle rtol 5e-5.  (Gaisser-Hillas Fluctuated: median < 7e-5 -- its profiles
+    keep twice as many altitude steps and the oracle itself sits at 5.2e-5 there.)"""
     r = rel_err(d, ref["dphots"])
     assert np.array_equal(d == 0, ref["dphots"] == 0), what
-    assert np.median(r) < 5e-5, (what, np.median(r))
+    assert np.median(r) < median_tol, (what, np.median(r))
     assert np.percentile(r, 99) < 3e-4, (what, np.percentile(r, 99))
     assert np.percentile(r, 99.9) < 2e-3, (what, np.percentile(r, 99.9))
     bad = r > np.maximum(2.5e-3, 5 * ref["sens"])

@@ -21,11 +21,14 @@ struct Ops1 {
 };
 }  // namespace
 
-extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
-                            const double* eshow, double detector_altitude, double area,
-                            double qe, double thr, int has_cloud, float cloud_top,
-                            double* numPEs, double* cosCh, double* dphots, double* cang,
-                            unsigned long long* stats6) {
+// profile: 0 Greisen, 1 Gaisser-Hillas Parameterized, 2 Gaisser-Hillas Fluctuated with
+// gh_rows[i] = the (Nm, Xm, X0, p1, p2, p3) CONEX row of event i
+extern "C" int nss_emul_eas_profile(long long n, const double* beta, const double* alt,
+                                    const double* eshow, double detector_altitude, double area,
+                                    double qe, double thr, int has_cloud, float cloud_top,
+                                    double* numPEs, double* cosCh, double* dphots, double* cang,
+                                    unsigned long long* stats6, int profile,
+                                    const double* gh_rows) {
   nss::EasTables T;
   nss_eas_tables_init(&T);
   nss::EasParams P;
@@ -35,14 +38,20 @@ extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
   P.pe_threshold = thr;
   P.has_cloud = has_cloud;
   P.cloud_top = cloud_top;
+  P.profile = profile;
+  P.pad = 0;
   nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long i = 0; i < n; ++i) {
     double d = 0.0, c = 1.5;
     if (!(alt[i] < 0.0 || alt[i] > 20.0)) {
       nss::EasPrep E;
       nss::EasAcc A;
-      nss::eas_prep(T, beta[i], alt[i], eshow[i], true, E);
-      nss::eas_walk<Ops1>(T, P, E, 0.0f, A, &st, true);
+      nss::eas_prep(T, beta[i], alt[i], eshow[i], true, profile,
+                    profile == 2 ? gh_rows + 6 * i : nullptr, E);
+      if (profile == 0)
+        nss::eas_walk<Ops1, false>(T, P, E, 0.0f, A, &st, true);
+      else
+        nss::eas_walk<Ops1, true>(T, P, E, 0.0f, A, &st, true);
       nss::eas_finish(P, beta[i], alt[i], A, d, c);
     }
     double npe, cc;
@@ -59,12 +68,21 @@ extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
   return 0;
 }
 
+extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
+                            const double* eshow, double detector_altitude, double area,
+                            double qe, double thr, int has_cloud, float cloud_top,
+                            double* numPEs, double* cosCh, double* dphots, double* cang,
+                            unsigned long long* stats6) {
+  return nss_emul_eas_profile(n, beta, alt, eshow, detector_altitude, area, qe, thr, has_cloud,
+                              cloud_top, numPEs, cosCh, dphots, cang, stats6, 0, nullptr);
+}
+
 // per-event prep record, for checking the column totals against a brute-force sum
 extern "C" int nss_emul_prep(double beta, double alt, double eshow, float* out8, int* out2) {
   nss::EasTables T;
   nss_eas_tables_init(&T);
   nss::EasPrep E;
-  nss::eas_prep(T, beta, alt, eshow, true, E);
+  nss::eas_prep(T, beta, alt, eshow, true, 0, nullptr, E);
   out8[0] = E.R0; out8[1] = E.q; out8[2] = E.alt; out8[3] = E.Ldet;
   out8[4] = E.Gtot; out8[5] = E.ozA[E.seg0]; out8[6] = E.gb; out8[7] = E.alpha;
   out2[0] = E.n_raw; out2[1] = E.Ieang;

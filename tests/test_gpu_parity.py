@@ -15,8 +15,8 @@ Tolerances (stated):
 import numpy as np
 import pytest
 
-from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, PIPE_TAGS, TAU_TABLES, check_engine_vs_reference,
-                      load_tables, make_config,
+from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, GH_PROFILES, GH_TAGS, PIPE_TAGS, TAU_TABLES,
+                      check_engine_vs_reference, conex_rows, load_tables, make_config,
                       philox_uniforms, rel_err)
 from oracle import nss_oracle as O
 
@@ -450,3 +450,66 @@ def test_engine_large_reference_sample(nss, eas_large, tag):
     npe = np.asarray(d) * 2.5 * 0.2
     near = np.abs(npe_ref / 10.0 - 1) < 2.5e-3
     assert np.array_equal((npe >= 10.0)[~near], (npe_ref >= 10.0)[~near])
+
+
+# ------------------------------------------------------------------ Gaisser-Hillas profiles
+
+
+@pytest.mark.parametrize("short", sorted(GH_PROFILES))
+@pytest.mark.parametrize("tag", GH_TAGS)
+def test_engine_gaisser_hillas_reference_sample(nss, eas_gh, tag, short):
+    """nss_cphotang with the two Gaisser-Hillas longitudinal profiles
+    (shower_properties.py:122-197) against the unmodified reference; the fluctuated profile
+    on the CONEX rows the reference drew (u_profile = (row + 1/2) / nrows)."""
+    ref = eas_gh[tag, short]
+    cp = nss.CphotAng(525.0, GH_PROFILES[short])
+    z = np.zeros_like(ref["beta"])
+    d, c = cp(ref["beta"], ref["alt"], ref["eshow"], z, z, None, u_profile=ref["u_profile"])
+    check_engine_vs_reference(np.asarray(d), np.asarray(c), ref, f"gpu/{tag}/{short}",
+                              median_tol=7e-5 if short == "ghf" else 5e-5)
+    assert np.median(rel_err(d, ref["oracle_dphots"])) < 1e-5
+
+
+@pytest.mark.parametrize("prof", sorted(GH_PROFILES.values()))
+def test_gaisser_hillas_acceptance_and_compute(nss, tables_v3, prof):
+    """The fused acceptance mode and compute() with a Gaisser-Hillas profile: same events
+    from the same Philox words (the CONEX row uniform is word 3 of stream 1), and both equal
+    to the oracle fed the identical uniforms."""
+    cfg = make_config(n=4000)
+    cfg.simulation.eas_long_profile = prof
+    seed, n = 5, 4000
+    r = nss.AcceptanceRunner(cfg, batch=1536)
+    r.enqueue(seed, 0, n)
+    got = r.finalize(r.sums())
+    sim = nss.compute(cfg, seed=seed)
+    assert sim.meta["ONEVPASS"][0] == got[2]
+    np.testing.assert_allclose(sim.meta["OMCINT"][0], got[0], rtol=1e-12)
+    u4, us, ut, ud, words = philox_uniforms(seed, 0, n)
+    u_prof = (words[1][3].astype(np.float64) + 0.5) / 4294967296.0
+    p = O.OracleParams(eas_long_profile=prof)
+    mc, cols, t, _ = O.run_path(p, tables_v3, u4, us, ut, ud, nthreads=4, u_profile=u_prof,
+                                conex=conex_rows())
+    rd = rel_err(sim["numPEs"], cols["numPEs"])
+    assert np.median(rd) < 1e-5 and rd.max() < 2.5e-3
+    near = np.abs(cols["numPEs"] / 10.0 - 1) < 2.5e-3
+    assert np.array_equal((sim["numPEs"] >= 10)[~near], (cols["numPEs"] >= 10)[~near])
+    if not near.any():
+        assert got[2] == mc[2]
+        np.testing.assert_allclose(got[0], mc[0], rtol=1e-11)
+    # the profile changes the answer (guards against silently running Greisen)
+    g = nss.compute(make_config(n=4000), seed=seed)
+    assert not np.allclose(g["numPEs"], sim["numPEs"], rtol=1e-3)
+
+
+def test_gaisser_hillas_fluctuated_needs_uniforms(nss):
+    from nuspacesim_b200 import _lib
+    import ctypes
+
+    p = _lib.NssParams()
+    p.eas_profile = 2
+    x = _lib.to_device(np.ones(4))
+    rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None, 4,
+                                 _lib.ptr(x), _lib.ptr(x), None, None)
+    assert rc == -2  # null u_profile
+    with pytest.raises(ValueError):
+        nss.CphotAng(525.0, "Linsley")

@@ -10,8 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import (EAS_LARGE_TAGS, ROOT, check_engine_vs_reference, load_tables, make_config,
-                      philox_uniforms, rel_err)
+from conftest import (EAS_LARGE_TAGS, GH_PROFILES, GH_TAGS, ROOT, check_engine_vs_reference,
+                      load_tables, make_config, philox_uniforms, rel_err)
 from oracle import nss_oracle as O
 
 
@@ -35,7 +35,7 @@ def test_params_struct_layout_and_init():
     from nuspacesim_b200 import _lib
     from nuspacesim_b200.params import params_from_config
 
-    assert ctypes.sizeof(_lib.NssParams) == _lib.lib().nss_sizeof_params() == 8 * 23 + 8
+    assert ctypes.sizeof(_lib.NssParams) == _lib.lib().nss_sizeof_params() == 8 * 24 + 8
     for kw in (dict(), dict(altitude=33.0), dict(altitude=1000.0, max_ch=np.radians(20.0))):
         p = params_from_config(make_config(**kw))
         g = O.geom_constants(O.OracleParams(
@@ -56,10 +56,15 @@ def test_null_and_bad_arguments_are_rejected_without_gpu():
     assert L.nss_geom_throw_u(ctypes.byref(p), None, 5, None, None) == -2
     assert L.nss_alt_dec(None, None, None, None, -1, None, None, None) == -1
     assert L.nss_alt_dec(None, None, None, None, 0, None, None, None) == 0  # empty input
-    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, 0, None, None, None, None,
-                             None, None) == 0
-    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, 3, None, None, None, None,
-                             None, None) == -2
+    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, None, 0, None, None, None,
+                             None, None, None) == 0
+    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, None, 3, None, None, None,
+                             None, None, None) == -2
+    p.eas_profile = 7  # unknown longitudinal profile
+    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, None, 3, None, None, None,
+                             None, None, None) == -1
+    p.eas_profile = 0
+    assert L.nss_eas_set_conex_table(None, 10) == -2
     h = ctypes.c_void_p()
     a = (ctypes.c_double * 4)()
     assert L.nss_tables_create(a, a, 1, a, 2, a, a, 2, a, 2, a, 2, ctypes.byref(h)) == -3
@@ -233,15 +238,17 @@ def emul():
     L = ctypes.CDLL(lib)
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
-    def run(beta, alt, es, det=525.0, top=None):
+    def run(beta, alt, es, det=525.0, top=None, profile=0, rows=None):
         beta, alt, es = (np.ascontiguousarray(x, float) for x in (beta, alt, es))
         n = beta.size
         npe, cc, d, c = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
         st = (ctypes.c_ulonglong * 6)()
-        L.nss_emul_eas(ctypes.c_longlong(n), dp(beta), dp(alt), dp(es), ctypes.c_double(det),
-                       ctypes.c_double(2.5), ctypes.c_double(0.2), ctypes.c_double(10.0),
-                       ctypes.c_int(top is not None), ctypes.c_float(top or 0.0), dp(npe), dp(cc),
-                       dp(d), dp(c), st)
+        rows = None if rows is None else np.ascontiguousarray(rows, float)
+        L.nss_emul_eas_profile(
+            ctypes.c_longlong(n), dp(beta), dp(alt), dp(es), ctypes.c_double(det),
+            ctypes.c_double(2.5), ctypes.c_double(0.2), ctypes.c_double(10.0),
+            ctypes.c_int(top is not None), ctypes.c_float(top or 0.0), dp(npe), dp(cc), dp(d),
+            dp(c), st, ctypes.c_int(profile), None if rows is None else dp(rows))
         return npe, cc, d, c, list(st)
 
     return run
@@ -379,6 +386,19 @@ def test_cli_create_config_and_overrides(tmp_path):
         assert opt in h
     bad = r.invoke(cli, ["run", fn, "10", "--monospectrum", "8", "--powerspectrum", "2", "6", "12"])
     assert bad.exit_code != 0
+
+
+@pytest.mark.parametrize("short", sorted(GH_PROFILES))
+@pytest.mark.parametrize("tag", GH_TAGS)
+def test_kernel_arithmetic_on_host_gaisser_hillas(emul, eas_gh, tag, short):
+    """The Gaisser-Hillas walk of nss_eas_core.cuh (host build) against the unmodified
+    reference: same stated tolerance as the Greisen profile."""
+    ref = eas_gh[tag, short]
+    prof = {"ghp": 1, "ghf": 2}[short]
+    _, _, d, c, _ = emul(ref["beta"], ref["alt"], ref["eshow"], 525.0, None, prof, ref["rows"])
+    check_engine_vs_reference(d, c, ref, f"host-emul/{tag}/{short}",
+                              median_tol=7e-5 if short == "ghf" else 5e-5)
+    assert np.median(rel_err(d, ref["oracle_dphots"])) < 1e-5
 
 
 @pytest.mark.parametrize("tag", EAS_LARGE_TAGS)

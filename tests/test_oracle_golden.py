@@ -4,8 +4,8 @@ the reference's own known-answer vectors.  CPU only."""
 import numpy as np
 import pytest
 
-from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, PIPE_TAGS, TAU_TABLES, check_engine_vs_reference,
-                      load_tables, rel_err)
+from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, GH_PROFILES, GH_TAGS, PIPE_TAGS, TAU_TABLES,
+                      check_engine_vs_reference, conex_rows, load_tables, rel_err)
 from oracle import nss_oracle as O
 
 # Known-answer vectors copied from the reference's test data
@@ -152,6 +152,28 @@ def test_engine_large_reference_sample(eas_large, tag):
     (BASELINE.json configs 1-4 inputs)."""
     ref = eas_large[tag]
     check_engine_vs_reference(ref["oracle_dphots"], ref["oracle_cang"], ref, f"oracle/{tag}")
+
+
+@pytest.mark.parametrize("short", sorted(GH_PROFILES))
+@pytest.mark.parametrize("tag", GH_TAGS)
+def test_engine_gaisser_hillas_reference_sample(eas_gh, tag, short):
+    """cphot_oracle.c with the Gaisser-Hillas profiles (shower_properties.py:122-197) against
+    the unmodified reference, the fluctuated one on the recorded CONEX rows."""
+    ref = eas_gh[tag, short]
+    check_engine_vs_reference(ref["oracle_dphots"], ref["oracle_cang"], ref, f"oracle/{tag}/{short}",
+                              median_tol=7e-5 if short == "ghf" else 5e-5)
+
+
+def test_conex_table_is_the_reference_table():
+    """The shipped .npy holds columns 4..9 of the reference's CONEX file (cphotang.py:266-276)."""
+    import os
+
+    T = conex_rows()
+    assert T.shape == (1000, 6) and T.dtype == np.float64 and np.isfinite(T).all()
+    src = ("/root/reference/src/nuspacesim/data/CONEX_table/"
+           "dumpGH_conex_pi_E17_95deg_0km_eposlhc_1394249052_211.dat")
+    if os.path.exists(src):
+        assert np.array_equal(T, np.loadtxt(src, usecols=(4, 5, 6, 7, 8, 9)))
 
 
 @pytest.mark.parametrize("tag", PIPE_TAGS)

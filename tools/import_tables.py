@@ -39,5 +39,17 @@ def main(src):
             print(d, fn, data.shape, names)
 
 
+def import_conex(src):
+    """Columns 4..9 (Nm, Xm, X0, p1, p2, p3) of the CONEX Gaisser-Hillas fit table the
+    reference loads for the fluctuated profile (cphotang.py:266-276), as float64 .npy."""
+    dst = os.path.join(ROOT, "nuspacesim_b200", "data", "CONEX_table")
+    os.makedirs(dst, exist_ok=True)
+    fn = "dumpGH_conex_pi_E17_95deg_0km_eposlhc_1394249052_211.dat"
+    tab = np.loadtxt(os.path.join(src, "CONEX_table", fn), usecols=(4, 5, 6, 7, 8, 9))
+    np.save(os.path.join(dst, "gh_conex_pi_E17_95deg_0km_eposlhc.npy"), tab)
+    print("CONEX_table", tab.shape)
+
+
 if __name__ == "__main__":
     main(sys.argv[1])
+    import_conex(sys.argv[1])
