@@ -461,6 +461,33 @@ def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nt
     return d, c, {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 
+def conditioning(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nthreads=1,
+                 profile="Greisen", gh_rows=None):
+    """How much the REFERENCE's photon density of each event moves under perturbations of
+    the size of its own float32 noise (tests use it to bound what no float32 implementation
+    can reproduce): max relative change over (a) shower energy x (1 + 1e-5) -- an event whose
+    first retained step has e2hill = 1150 + 454 ln s barely above 0 (cphotang.py:561-564,
+    weights ~ 1/e2hill) -- and (b) every distance-to-detector x (1 +- 2e-6) -- a step whose
+    quantised solid angle (cphotang.py:469-474) sits on a rounding tie."""
+    kw = dict(detector_altitude=detector_altitude, cloud_top=cloud_top, nthreads=nthreads,
+              profile=profile, gh_rows=gh_rows)
+    es = np.asarray(eshow100pev, dtype=np.float64)
+    d0 = cphotang(beta, alt, es, **kw)[0]
+    with np.errstate(all="ignore"):
+        def rel(d):
+            r = np.abs(d - d0) / np.maximum(np.abs(d0), 1e-300)
+            r[d == d0] = 0
+            return r
+        sens = rel(cphotang(beta, alt, es * (1 + 1e-5), **kw)[0])
+        try:
+            for sc in (1 + 2e-6, 1 - 2e-6):
+                _lib().nss_oracle_set_dist_scale(ctypes.c_double(sc))
+                sens = np.maximum(sens, rel(cphotang(beta, alt, es, **kw)[0]))
+        finally:
+            _lib().nss_oracle_set_dist_scale(ctypes.c_double(1.0))
+    return sens
+
+
 def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1, gh_rows=None):
     """EAS.__call__ (eas.py:83-138) -> (numPEs, costhetaChEff, dphots, cang_deg, stats)."""
     beta = np.ascontiguousarray(beta, dtype=np.float64)
