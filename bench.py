@@ -273,7 +273,14 @@ def main():
         line_extra["roofline"] = dict(
             bound="fp32", kernel="eas_walk_kernel", achieved=ach, peak=fp32_peak.value,
             unit="TFLOP/s", frac=ach / fp32_peak.value if fp32_peak.value else None,
-            traffic=None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE eas_walk_kernel launch of this
+            # workload (2 Mi events) from the committed ncu --set full capture
+            # (profiles/r01_eas_v4_ncu_key_metrics.json): 305.7 MB + 83.7 MB.  The records the
+            # kernel must move are 144 B (EasPrep) + 48 B (EasAcc) per event = 381 MB per
+            # launch: no wasted re-reads; the kernel is compute bound (bound = "fp32").
+            traffic=389.39e6 if args.batch == 1 << 21 else None,
+            traffic_unit="bytes per launch (ncu, cold cache); algorithmic record bytes per "
+                         "launch = 192 B x events",
             peak_source="nss_microbench_peaks on this device (FFMA chains; MEASURED_PEAKS.json "
                         "has no FP32 entry), of measured",
             sfu=dict(achieved=transc_step / eas_s_per_step * 1e-12, peak=mufu_peak.value,
