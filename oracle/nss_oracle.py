@@ -73,6 +73,8 @@ class OracleParams:
     spec_upper: float = 12.0
     cloud_top: Optional[float] = None  # None == NoCloud (cloudf is constant 0 -> see eas())
     eas_long_profile: str = "Greisen"  # config.simulation.eas_long_profile
+    # PressureMapCloud: the month's (361, 576) cloud-top pressure map [Pa]; overrides cloud_top
+    cloud_map: Optional[np.ndarray] = None
 
 
 # --------------------------------------------------------------------------- geometry
@@ -437,6 +439,59 @@ def _profile_args(profile, gh_rows, n):
     return ctypes.c_int(kind), None, None
 
 
+def _cloud_args(cloud_top, n):
+    """cloud_top: None (no cloudf), a scalar (NoCloud/MonoCloud: np.single) or a length-n
+    array of per-event float64 cloud tops (PressureMapCloud) -> (has_cloud, scalar, array)."""
+    if cloud_top is None:
+        return ctypes.c_int(0), ctypes.c_float(0.0), None, None
+    if np.ndim(cloud_top) == 0:
+        return ctypes.c_int(1), ctypes.c_float(float(cloud_top)), None, None
+    ev = np.ascontiguousarray(cloud_top, dtype=np.float64)
+    if ev.shape != (n,):
+        raise ValueError("per-event cloud tops must have one entry per event")
+    return ctypes.c_int(1), ctypes.c_float(0.0), _dp(ev), ev
+
+
+# 1976 US Standard Atmosphere layers (src/nuspacesim/constants.py:55-75)
+_STD_H = np.array([0, 11, 20, 32, 47, 51, 71, 84.852, np.inf])
+_STD_L = np.array([-6.5, 0.0, 1.0, 2.8, 0.0, -2.8, -2.0, 0.0, 0.0])
+_STD_T = np.array([288.15, 216.65, 216.65, 228.65, 270.65, 270.65, 214.65, 186.946, 0.0])
+_STD_P = 1.01325e5 * np.array([1.0, 2.233611e-1, 5.403295e-2, 8.5666784e-3, 1.0945601e-3,
+                               6.6063531e-4, 3.9046834e-5, 3.68501e-6, 0.0])
+_STD_GMR = 34.163195
+_STD_RE = 6371.0  # constants.py:48
+
+
+def std_atm_altitude_from_pressure(P):
+    """atmospheric_models.py:105-123: geometric altitude [km] of pressure P [Pa]."""
+    P = np.asarray(P, dtype=np.float64)
+    i = np.zeros(P.shape, dtype=int)
+    for j in range(1, len(_STD_P)):
+        i[_STD_P[j] >= P] = j
+    H = _STD_H[i].astype(np.float64)
+    pos = P > 0
+    iso = _STD_L[i] == 0
+    with np.errstate(all="ignore"):
+        h_iso = _STD_T[i] * (1.0 / _STD_GMR) * np.log(_STD_P[i] / P)
+        h_grad = (_STD_T[i] / _STD_L[i]) * ((_STD_P[i] / P) ** ((1.0 / _STD_GMR) * _STD_L[i]) - 1)
+    H = np.where(pos & iso, H + h_iso, np.where(pos & ~iso, H + h_grad, H))
+    with np.errstate(all="ignore"):
+        z = _STD_RE * H / (_STD_RE - H)
+    return np.where(pos, z, np.inf)
+
+
+def cloud_top_pressure_map(pressure_map, lat, long=None):
+    """clouds.py:85-96 altitude_from_pressure_map_v0 for arrays of (lat, long), reproducing
+    the reference as written: BOTH map indices come from `lat` (searchsorted(longitudes,
+    lat), :92), and compute() passes latitudes in radians (region_geometry.py:351) to axes
+    laid out in degrees."""
+    m = np.asarray(pressure_map)
+    lat = np.asarray(lat, dtype=np.float64)
+    i = np.searchsorted(np.linspace(-90, 90, m.shape[0]), lat)
+    j = np.searchsorted(np.linspace(-180, 180, m.shape[1]), lat)
+    return std_atm_altitude_from_pressure(m[i, j])
+
+
 def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nthreads=1,
              profile="Greisen", gh_rows=None):
     """CphotAng.__call__ (cphotang.py:703-724) -> (dphots, cang_deg, stats).
@@ -452,12 +507,11 @@ def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nt
     st = _Stats()
     t = _ctables()
     kind, rows_p, _keep = _profile_args(profile, gh_rows, n)
+    hc, ctop, cev_p, _keep2 = _cloud_args(cloud_top, n)
     _lib().nss_oracle_cphotang_profile(
-        ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es),
-        ctypes.c_int(cloud_top is not None),
-        ctypes.c_float(0.0 if cloud_top is None else cloud_top),
+        ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es), hc, ctop,
         ctypes.c_double(detector_altitude), _dp(d), _dp(c), ctypes.byref(st),
-        ctypes.c_int(nthreads), kind, rows_p)
+        ctypes.c_int(nthreads), kind, rows_p, cev_p)
     return d, c, {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 
@@ -488,8 +542,9 @@ def conditioning(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None
     return sens
 
 
-def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1, gh_rows=None):
-    """EAS.__call__ (eas.py:83-138) -> (numPEs, costhetaChEff, dphots, cang_deg, stats)."""
+def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1, gh_rows=None, cloud_ev=None):
+    """EAS.__call__ (eas.py:83-138) -> (numPEs, costhetaChEff, dphots, cang_deg, stats).
+    ``cloud_ev``: per-event cloud tops (PressureMapCloud), overriding ``p.cloud_top``."""
     beta = np.ascontiguousarray(beta, dtype=np.float64)
     alt = np.ascontiguousarray(altDec, dtype=np.float64)
     es = np.ascontiguousarray(showerEnergy, dtype=np.float64)
@@ -498,14 +553,13 @@ def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1, gh_rows=None):
     st = _Stats()
     t = _ctables()
     kind, rows_p, _keep = _profile_args(getattr(p, "eas_long_profile", "Greisen"), gh_rows, n)
+    hc, ctop, cev_p, _keep2 = _cloud_args(p.cloud_top if cloud_ev is None else cloud_ev, n)
     _lib().nss_oracle_eas_profile(
-        ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es),
-        ctypes.c_int(p.cloud_top is not None),
-        ctypes.c_float(0.0 if p.cloud_top is None else p.cloud_top),
+        ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es), hc, ctop,
         ctypes.c_double(p.detector_altitude), ctypes.c_double(p.telescope_effective_area),
         ctypes.c_double(p.quantum_efficiency), ctypes.c_double(p.photo_electron_threshold),
         _dp(npe), _dp(cth), _dp(d), _dp(c), ctypes.byref(st), ctypes.c_int(nthreads), kind,
-        rows_p)
+        rows_p, cev_p)
     return npe, cth, d, c, {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 
@@ -537,7 +591,13 @@ def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1, u_pr
         idx = np.minimum((np.asarray(u_profile)[m] * conex.shape[0]).astype(np.int64),
                          conex.shape[0] - 1)
         rows = conex[idx]
-    npe, cth, d, c, st = eas(p, beta, alt, sh, nthreads=nthreads, gh_rows=rows)
+    cloud_ev = None
+    if getattr(p, "cloud_map", None) is not None:
+        # compute.py:214-216: cloudf(init_lat, init_long) at the ground spot of each trajectory
+        lat0, _ = geom_lat_long(g, t, np.zeros(int(m.sum())))
+        cloud_ev = cloud_top_pressure_map(p.cloud_map, lat0)
+    npe, cth, d, c, st = eas(p, beta, alt, sh, nthreads=nthreads, gh_rows=rows,
+                             cloud_ev=cloud_ev)
     mc = mcintegral(g, t, npe, cth, pex, p.photo_electron_threshold, sn, sw)
     cols = dict(beta_rad=beta, theta_rad=t["thetaTrSubV"][m], path_len=t["losPathLen"][m],
                 log_e_nu=le, tauBeta=tb, tauLorentz=lor, tauEnergy=te, showerEnergy=sh,
