@@ -186,6 +186,29 @@ def to_device(x, dtype="float64"):
     return torch.from_numpy(a).to("cuda", non_blocking=False)
 
 
+_H2D_STREAM = None
+
+
+def to_device_prefetch(x, dtype="float64"):
+    """Start the host -> device copy of `x` on a side stream and return (tensor, event): the
+    copy of a PINNED host tensor overlaps whatever runs on the current stream; the consumer
+    calls ``torch.cuda.current_stream().wait_event(event)`` before its first use.  Anything
+    that is not a pinned torch tensor takes the plain synchronous path (event = None)."""
+    global _H2D_STREAM
+    torch = torch_cuda()
+    if not (hasattr(x, "is_pinned") and not x.is_cuda and x.is_pinned()
+            and x.dtype == getattr(torch, dtype) and x.is_contiguous()):
+        return to_device(x, dtype), None
+    if _H2D_STREAM is None:
+        _H2D_STREAM = torch.cuda.Stream()
+    with torch.cuda.stream(_H2D_STREAM):
+        t = x.to("cuda", non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(_H2D_STREAM)
+    t.record_stream(torch.cuda.current_stream())
+    return t, ev
+
+
 def empty(n, dtype="float64"):
     torch = torch_cuda()
     return torch.empty(int(n), dtype=getattr(torch, dtype), device="cuda")
@@ -207,6 +230,7 @@ class _HostSink:
         torch = torch_cuda()
         self.stream = torch.cuda.Stream()
         self.deferred = 0
+        self.pending_checks = []
 
     def copy(self, t) -> np.ndarray:
         torch = torch_cuda()
@@ -225,8 +249,16 @@ class _HostSink:
             self.stream.synchronize()
         return out.numpy()  # the array keeps the pinned tensor alive
 
+    def defer_check(self, flags, raiser):
+        """Error flags of a kernel are read back with everything else at the end of the
+        deferred region instead of stalling the pipeline behind queued column copies."""
+        self.pending_checks.append((flags, raiser))
+
     def synchronize(self):
         self.stream.synchronize()
+        checks, self.pending_checks = self.pending_checks, []
+        for flags, raiser in checks:
+            raiser(flags)
 
 
 _SINK = None

@@ -86,10 +86,20 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
 
     sw = StagedWriter(sim, sink, output_file, write_stages)
     U = uniforms or {}
+    # Pinned host uniforms: u4 goes first (geometry needs it), the per-stage ones follow on a
+    # side stream and overlap the geometry kernels.
+    Ud = {}
+    for name in ("u4", "u_spec", "u_tau", "u_dec", "u_profile"):
+        if name in U:
+            Ud[name] = _lib.to_device_prefetch(U[name])
 
     logv(f"Running NuSpaceSim with Energy Spectrum ({config.simulation.spectrum})")
     logv("Computing Geometries.")
-    thrown = U["u4"] if "u4" in U else config.simulation.thrown_events
+    thrown = config.simulation.thrown_events
+    if "u4" in U:
+        thrown, ev = Ud["u4"]
+        if ev is not None:
+            _lib.torch_cuda().cuda.current_stream().wait_event(ev)
     beta_tr, thetaArr, pathLenArr, *_ = geom(thrown, store=sw, plot=to_plot, device=True)
     n_valid = int(beta_tr.numel())
     logv(f"\tThrew {config.simulation.thrown_events} neutrinos. {n_valid} were valid.")
@@ -98,7 +108,6 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
         return sim
 
     torch = _lib.torch_cuda()
-    mask = geom._dev["event_mask"].bool()
 
     WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2, "u_profile": 3}
 
@@ -106,8 +115,11 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
         """Per-valid-event uniforms: the caller's array, else (when the geometry itself came
         from Philox) the event's own counter-based stream, so that compute(seed=s) and
         run_acceptance(seed=s) simulate identical events."""
-        if name in U:
-            return _lib.to_device(U[name])[mask]
+        if name in Ud:
+            full, ev = Ud[name]
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+            return geom.compact(full)
         if "u4" not in U:
             return geom.event_uniforms(WHICH[name])
         return None

@@ -104,6 +104,22 @@ class RegionGeom:
         )
         self._n_valid = int(nset.item())
 
+    def compact(self, full, device: bool = True):
+        """Entries of a length-N (thrown-order) array that belong to valid events, in thrown
+        order -- ``full[event_mask]`` without the host synchronisation of boolean indexing
+        (the positions are known from the scan throw() already did)."""
+        f = _lib.to_device(full)
+        if f.numel() != self._n:
+            raise RuntimeError(f"expected one entry per thrown event ({self._n}), got {f.numel()}")
+        out = _lib.empty(self._n_valid)
+        _lib.check(
+            _lib.lib().nss_compact_f64(
+                _lib.ptr(self._dev["event_mask"]), _lib.ptr(self._pos), _lib.ptr(f),
+                _lib.ptr(out), self._n, 0, _lib.stream_ptr()),
+            "nss_compact_f64",
+        )
+        return out if device else _lib.to_host(out)
+
     def event_uniforms(self, which: int, device: bool = True):
         """Uniform `which` (0 spectrum, 1 tau energy, 2 decay length) of every VALID event's
         Philox stream, in thrown order: the numbers the column-free mode draws in-kernel for

@@ -30,24 +30,49 @@ def _f64p(a):
     return a.ctypes.data_as(_lib.c_f64p)
 
 
+# compute() builds a Taus per call: the parsed table files and their device copies are kept
+# per process.  Cached grids are shared between instances (treat them as read-only; assign
+# a new NssGrid to ``pexit_grid`` / ``tau_cdf_grid`` to use other tables -- that instance
+# then uploads and owns its own copy).
+_GRID_CACHE = {}
+_HANDLE_CACHE = {}
+
+
+def _read_tables(tid, ver):
+    key = (str(tid), str(ver))
+    if key not in _GRID_CACHE:
+        d = os.path.join(_DATA, f"{tid}_tables")
+        _GRID_CACHE[key] = (
+            NssGrid.read(os.path.join(d, f"nu2tau_pexit.{ver}.h5"), path="/", format="hdf5"),
+            NssGrid.read(os.path.join(d, f"nu2tau_cdf.{ver}.h5"), format="hdf5"))
+    return _GRID_CACHE[key]
+
+
 class Taus:
     def __init__(self, config, seed: int = 0):
         self.config = config
         self.params = params_from_config(config)
         tid = config.simulation.tau_shower.id
         ver = config.simulation.tau_shower.table_version
-        d = os.path.join(_DATA, f"{tid}_tables")
-        self.pexit_grid = NssGrid.read(os.path.join(d, f"nu2tau_pexit.{ver}.h5"), path="/",
-                                       format="hdf5")
-        self.tau_cdf_grid = NssGrid.read(os.path.join(d, f"nu2tau_cdf.{ver}.h5"), format="hdf5")
+        self.pexit_grid, self.tau_cdf_grid = _read_tables(tid, ver)
+        self._cached = (self.pexit_grid, self.tau_cdf_grid)
         self._rng = np.random.Generator(np.random.Philox(key=int(seed)))
         self._handle = None
+        self._owns_handle = False
 
     # device copy of the two grids
     @property
     def tables(self):
+        if self._handle is not None and not self._owns_handle and (
+                self.pexit_grid is not self._cached[0] or self.tau_cdf_grid is not self._cached[1]):
+            self._handle = None  # the grids were replaced after the shared copy was taken
         if self._handle is None:
-            _lib.torch_cuda()
+            torch = _lib.torch_cuda()
+            shared = (self.pexit_grid is self._cached[0] and self.tau_cdf_grid is self._cached[1])
+            ckey = (id(self.pexit_grid), id(self.tau_cdf_grid), torch.cuda.current_device())
+            if shared and ckey in _HANDLE_CACHE:
+                self._handle = _HANDLE_CACHE[ckey]
+                return self._handle
             pg, cg = self.pexit_grid, self.tau_cdf_grid
             arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
                 pg.data, pg["log_e_nu"], pg["beta_rad"], cg.data, cg["log_e_nu"],
@@ -61,15 +86,28 @@ class Taus:
                 "nss_tables_create",
             )
             self._handle = h
+            self._owns_handle = not shared
+            if shared:
+                _HANDLE_CACHE[ckey] = h
         return self._handle
 
     def __del__(self):
         try:
-            if self._handle is not None:
+            if self._handle is not None and self._owns_handle:
                 _lib.lib().nss_tables_free(self._handle)
                 self._handle = None
         except Exception:
             pass
+
+    @staticmethod
+    def _check_flags(flags):
+        """Raise now, or -- inside compute()'s deferred region -- when its copies are drained
+        (a flag read-back would otherwise queue behind the column copies)."""
+        sink = _lib.host_sink()
+        if sink.deferred:
+            sink.defer_check(flags, Taus._raise_flags)
+        else:
+            Taus._raise_flags(flags)
 
     @staticmethod
     def _raise_flags(flags):
@@ -101,7 +139,7 @@ class Taus:
                                          _lib.ptr(out), _lib.ptr(flags), _lib.stream_ptr()),
             "nss_tau_exit_prob",
         )
-        self._raise_flags(flags)
+        self._check_flags(flags)
         return out if dev else _lib.to_host(out)
 
     def tau_energy(self, betas, log_e_nu, u=None):
@@ -117,7 +155,7 @@ class Taus:
                                       _lib.stream_ptr()),
             "nss_tau_energy",
         )
-        self._raise_flags(flags)
+        self._check_flags(flags)
         return out if dev else _lib.to_host(out)
 
     @decorators.nss_result_plot()
@@ -137,5 +175,5 @@ class Taus:
                                       _lib.ptr(flags), _lib.stream_ptr()),
             "nss_tau_sample",
         )
-        self._raise_flags(flags)
+        self._check_flags(flags)
         return tuple(outs) if dev else tuple(_lib.to_host(o) for o in outs)
