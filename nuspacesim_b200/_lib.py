@@ -98,10 +98,13 @@ SIGNATURES = {
     "nss_tau_sample": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
     "nss_alt_dec": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3),
-    "nss_eas_optical": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 5 + [C.c_int64] +
+    "nss_eas_optical": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 6 + [C.c_int64] +
                         [C.c_void_p] * 6),
-    "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 4 + [C.c_int64] +
+    "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 5 + [C.c_int64] +
                      [C.c_void_p] * 4),
+    "nss_cloud_set_altitude_map": (C.c_int, [c_f64p, C.c_int, C.c_int, c_f64p, c_f64p]),
+    "nss_cloud_top_from_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p]),
     "nss_eas_set_conex_table": (C.c_int, [c_f64p, C.c_int]),
     "nss_eas_profile_enable": (C.c_int, [C.c_int]),
     "nss_eas_profile_collect": (C.c_int, [c_f64p, c_i64p]),

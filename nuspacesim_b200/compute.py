@@ -181,6 +181,7 @@ class AcceptanceRunner:
             from .simulation.eas_optical import cphotang
 
             cphotang._ensure_conex_on_device()
+        self.cloud = CloudTopHeight(config) if self.params.has_cloud == 2 else None
         self.batch = int(batch)
         L = _lib.lib()
         self.ws = _lib.empty(int(L.nss_acceptance_workspace_bytes(self.batch)), "uint8")
@@ -191,6 +192,8 @@ class AcceptanceRunner:
 
     def enqueue(self, seed: int, first_event: int, n: int):
         """Accumulate events [first_event, first_event + n) into the device sums (async)."""
+        if self.cloud is not None:
+            self.cloud.register()  # the library holds one map per process
         _lib.check(
             _lib.lib().nss_run_acceptance(
                 C.byref(self.params), self.taus.tables, int(seed), int(first_event), int(n),

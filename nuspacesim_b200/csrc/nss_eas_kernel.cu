@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256)
 eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
                 const double* __restrict__ alt, const double* __restrict__ eshow,
                 const uint8_t* __restrict__ mask, const double* __restrict__ conex,
-                int conex_rows, const double* __restrict__ u_profile, long long n,
+                int conex_rows, const double* __restrict__ u_profile,
+                const double* __restrict__ cloud_ev, float cloud_run, long long n,
                 nss::EasPrep* __restrict__ prep) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -81,7 +82,8 @@ eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
       row = conex + 6 * (long long)r;
     }
     nss::EasPrep P;
-    nss::eas_prep(c_tables, beta[i], a, eshow[i], run, profile, row, P);
+    nss::eas_prep(c_tables, beta[i], a, eshow[i], run, profile, row,
+                  cloud_ev ? (float)cloud_ev[i] : cloud_run, P);
     prep[i] = P;
   }
 }
@@ -119,7 +121,9 @@ eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long lo
       dst[2] = __ldg(src + 2);
     }
     nss::EasAcc A;
-    nss::eas_walk<Ops32, GH>(c_tables, P, E, ozA_lane, A, stats ? &st : nullptr, lane == 0);
+    const float cloud_top = __shfl_sync(0xffffffffu, ozA_lane, 11);  // EasPrep::cloud
+    nss::eas_walk<Ops32, GH>(c_tables, P, E, ozA_lane, cloud_top, A, stats ? &st : nullptr,
+                             lane == 0);
     if (lane == 0) acc[i] = A;
   }
   if (stats && lane == 0 && st.n_events) {
@@ -136,13 +140,15 @@ eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long lo
 __global__ void __launch_bounds__(256)
 eas_finish_kernel(int mode, nss::EasParams P, const double* __restrict__ beta,
                   const double* __restrict__ alt, const nss::EasAcc* __restrict__ acc,
-                  long long n, double* __restrict__ out0, double* __restrict__ out1,
+                  const nss::EasPrep* __restrict__ prep, long long n,
+                  double* __restrict__ out0, double* __restrict__ out1,
                   double* __restrict__ dphots, double* __restrict__ cang) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const nss::EasAcc A = acc[i];
     double d = 0.0, c = 0.0;
-    nss::eas_finish(P, beta[i], alt[i], A, d, c);
+    const float cloud_top = P.has_cloud ? __ldg(&prep[i].cloud) : 0.0f;
+    nss::eas_finish(P, beta[i], alt[i], A, cloud_top, d, c);
     if (mode == 0) {
       if (A.pad == 0) c = 1.5;  // eas.py:106-107 default for events the mask skipped
       double npe, cc;
@@ -202,14 +208,17 @@ ProfRec* g_prof = nullptr;
 int g_prof_n = 0, g_prof_cap = 0;
 
 int launch(int mode, const NssParams* p, const double* beta, const double* alt,
-           const double* eshow, const uint8_t* mask, const double* u_profile, int64_t n,
-           double* o0, double* o1, double* dph, double* cang, unsigned long long* stats,
-           void* stream) {
+           const double* eshow, const uint8_t* mask, const double* u_profile,
+           const double* cloud_ev, int64_t n, double* o0, double* o1, double* dph, double* cang,
+           unsigned long long* stats, void* stream) {
   if (!p) return NSS_E_NULL;
-  if (n < 0 || p->eas_profile < 0 || p->eas_profile > 2) return NSS_E_BADARG;
+  if (n < 0 || p->eas_profile < 0 || p->eas_profile > 2 || p->has_cloud < 0 || p->has_cloud > 2)
+    return NSS_E_BADARG;
   if (n == 0) return 0;
   if (!beta || !alt || !eshow || !o0 || !o1) return NSS_E_NULL;
   if (p->eas_profile == 2 && (!u_profile || !g_conex)) return NSS_E_NULL;
+  if (p->has_cloud == 2 && !cloud_ev) return NSS_E_NULL;
+  if (p->has_cloud != 2) cloud_ev = nullptr;
   const bool gh = p->eas_profile != 0;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t err;
@@ -249,7 +258,8 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
   err = cudaMemsetAsync(g_scr.counter, 0, 8, s);
   if (err != cudaSuccess) return (int)err;
   eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, p->eas_profile, beta, alt, eshow, mask, g_conex,
-                                         g_conex_rows, u_profile, n, g_scr.prep);
+                                         g_conex_rows, u_profile, cloud_ev, P.cloud_top, n,
+                                         g_scr.prep);
 
   long long need = (n + (WALK_BLOCK / 32) - 1) / (WALK_BLOCK / 32);
   int blocks = (int)(need < g_walk_blocks[gh] ? need : g_walk_blocks[gh]);
@@ -271,7 +281,8 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     eas_walk_kernel<false><<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc,
                                                          g_scr.counter, stats);
   if (rec) cudaEventRecord(rec->b, s);
-  eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, g_scr.acc, n, o0, o1, dph, cang);
+  eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, g_scr.acc, g_scr.prep, n, o0, o1,
+                                           dph, cang);
   return (int)cudaGetLastError();
 }
 
@@ -279,19 +290,19 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
 
 extern "C" int nss_eas_optical(const NssParams* p, const double* beta, const double* altDec,
                                const double* showerEnergy, const uint8_t* mask,
-                               const double* u_profile, int64_t n, double* numPEs,
-                               double* costhetaChEff, double* dphots, double* cang,
-                               unsigned long long* stats, void* stream) {
-  return launch(0, p, beta, altDec, showerEnergy, mask, u_profile, n, numPEs, costhetaChEff,
-                dphots, cang, stats, stream);
+                               const double* u_profile, const double* cloud_top_ev, int64_t n,
+                               double* numPEs, double* costhetaChEff, double* dphots,
+                               double* cang, unsigned long long* stats, void* stream) {
+  return launch(0, p, beta, altDec, showerEnergy, mask, u_profile, cloud_top_ev, n, numPEs,
+                costhetaChEff, dphots, cang, stats, stream);
 }
 
 extern "C" int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
-                            const double* Eshow100PeV, const double* u_profile, int64_t n,
-                            double* dphots, double* cang, unsigned long long* stats,
-                            void* stream) {
-  return launch(1, p, betaE, alt, Eshow100PeV, nullptr, u_profile, n, dphots, cang, nullptr,
-                nullptr, stats, stream);
+                            const double* Eshow100PeV, const double* u_profile,
+                            const double* cloud_top_ev, int64_t n, double* dphots, double* cang,
+                            unsigned long long* stats, void* stream) {
+  return launch(1, p, betaE, alt, Eshow100PeV, nullptr, u_profile, cloud_top_ev, n, dphots,
+                cang, nullptr, nullptr, stats, stream);
 }
 
 extern "C" int nss_eas_set_conex_table(const double* rows_host, int nrows) {

@@ -158,6 +158,61 @@ geom_kernel(NssParams p, const double* __restrict__ u, uint64_t seed, uint64_t f
   }
 }
 
+// find_lat_long_along_traj (region_geometry.py:289-355) for one trajectory; longS/latS in
+// degrees as throw() stores them
+__device__ inline void lat_long_event(double R, double d, double th, double ph, double el,
+                                      double az, double lonS_deg, double latS_deg, double& lat_o,
+                                      double& lon_o) {
+  const double sth = sin(th), cth = cos(th), sph = sin(ph), cph = cos(ph);
+  const double se = sin(el), ce = cos(el), sa = sin(az), ca = cos(az);
+  const double lon = lonS_deg * (PI_D / 180.0), lat = latS_deg * (PI_D / 180.0);
+  const double slo = sin(lon), clo = cos(lon), sla = sin(lat), cla = cos(lat);
+  const double xv = d * sth * cph;
+  const double yv = d * sth * sph + R * ce;
+  const double zv = d * cth + R * se;
+  const double xn = -sa * xv - ca * se * yv + ca * ce * zv;
+  const double yn = ca * xv - sa * se * yv + sa * ce * zv;
+  const double zn = ce * yv + se * zv;
+  const double xe = -slo * xn - clo * sla * yn + clo * cla * zn;
+  const double ye = clo * xn - slo * sla * yn + slo * cla * zn;
+  const double ze = cla * yn + sla * zn;
+  const double rr = sqrt(xe * xe + ye * ye + ze * ze);
+  lat_o = asin(ze / rr);
+  lon_o = atan2(ye, xe);
+}
+
+// PressureMapCloud lookup (clouds.py:85-96): searchsorted (side = left) on both axes with the
+// LATITUDE, as the reference does; indices clamped to the map
+struct CloudMapView {
+  const double *alt, *lat_ax, *lon_ax;
+  int nlat, nlon;
+};
+
+__device__ inline int searchsorted_left(const double* __restrict__ ax, int n, double x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ax[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ inline double cloud_top_event(const CloudMapView& m, double lat) {
+  int i = searchsorted_left(m.lat_ax, m.nlat, lat);
+  int j = searchsorted_left(m.lon_ax, m.nlon, lat);
+  i = i < m.nlat ? i : m.nlat - 1;
+  j = j < m.nlon ? j : m.nlon - 1;
+  return m.alt[(size_t)i * m.nlon + j];
+}
+
+__global__ void __launch_bounds__(256)
+cloud_top_kernel(CloudMapView m, const double* __restrict__ lat, int64_t n,
+                 double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = cloud_top_event(m, lat[i]);
+}
+
 __global__ void __launch_bounds__(256)
 lat_long_kernel(NssParams p, const double* __restrict__ th, const double* __restrict__ ph,
                 const double* __restrict__ el, const double* __restrict__ az,
@@ -167,23 +222,8 @@ lat_long_kernel(NssParams p, const double* __restrict__ th, const double* __rest
   const double R = p.earth_radius;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const double d = dist[i];
-    const double sth = sin(th[i]), cth = cos(th[i]), sph = sin(ph[i]), cph = cos(ph[i]);
-    const double se = sin(el[i]), ce = cos(el[i]), sa = sin(az[i]), ca = cos(az[i]);
-    const double lon = lonS[i] * (PI_D / 180.0), lat = latS[i] * (PI_D / 180.0);
-    const double slo = sin(lon), clo = cos(lon), sla = sin(lat), cla = cos(lat);
-    const double xv = d * sth * cph;
-    const double yv = d * sth * sph + R * ce;
-    const double zv = d * cth + R * se;
-    const double xn = -sa * xv - ca * se * yv + ca * ce * zv;
-    const double yn = ca * xv - sa * se * yv + sa * ce * zv;
-    const double zn = ce * yv + se * zv;
-    const double xe = -slo * xn - clo * sla * yn + clo * cla * zn;
-    const double ye = clo * xn - slo * sla * yn + slo * cla * zn;
-    const double ze = cla * yn + sla * zn;
-    const double rr = sqrt(xe * xe + ye * ye + ze * ze);
-    lat_out[i] = asin(ze / rr);
-    lon_out[i] = atan2(ye, xe);
+    lat_long_event(R, dist[i], th[i], ph[i], el[i], az[i], lonS[i], latS[i], lat_out[i],
+                   lon_out[i]);
   }
 }
 
@@ -565,13 +605,14 @@ __global__ void mc_finish(double mcnorm, double n_thrown, const double* tmp, dou
 struct FrontBufs {
   double *beta, *alt, *shower, *fgeo, *ctrv, *pexit, *npe, *cth;
   double* uprof;  // CONEX row uniform (Philox stream 1, word 3): Gaisser-Hillas Fluctuated only
+  double* cloud;  // per-event cloud top: PressureMapCloud only
   uint8_t* mask;
 };
 
 // throw -> spectrum -> taus -> altDec for thrown events [first, first+n) from Philox.
 __global__ void __launch_bounds__(256)
-front_kernel(NssParams p, TabView t, uint64_t seed, uint64_t first, int64_t n, FrontBufs b,
-             int32_t* flags) {
+front_kernel(NssParams p, TabView t, CloudMapView cm, uint64_t seed, uint64_t first, int64_t n,
+             FrontBufs b, int32_t* flags) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t w0[4], w1[4];
@@ -597,6 +638,13 @@ front_kernel(NssParams p, TabView t, uint64_t seed, uint64_t first, int64_t n, F
     b.ctrv[i] = g.costhetaTrSubV;
     b.pexit[i] = to.tauExitProb;
     if (p.eas_profile == 2) b.uprof[i] = u01(w1[3]);
+    if (p.has_cloud == 2) {
+      // cloudf(init_lat, init_long) at the trajectory's ground spot (compute.py:214-216)
+      double lat0, lon0;
+      lat_long_event(p.earth_radius, 0.0, g.thetaTrSubV, g.phiTrSubV, g.elevAngVSubN,
+                     g.aziAngVSubN, g.longS, g.latS, lat0, lon0);
+      b.cloud[i] = cloud_top_event(cm, lat0);
+    }
   }
 }
 
@@ -634,6 +682,8 @@ __global__ void accept_fold(const double* partial, int nblocks, double n_batch, 
 }
 
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+CloudMapView g_cloud = {nullptr, nullptr, nullptr, 0, 0};  // nss_cloud_set_altitude_map
 
 void spec_norms(const NssParams* p, double& sn, double& sw) {
   // spectra.py:73-106
@@ -892,9 +942,48 @@ extern "C" int nss_mcintegral(const NssParams* p, const double* cTrN, const doub
   return (int)cudaGetLastError();
 }
 
+extern "C" int nss_cloud_set_altitude_map(const double* alt_map_host, int nlat, int nlon,
+                                          const double* lat_axis_host,
+                                          const double* lon_axis_host) {
+  if (!alt_map_host || !lat_axis_host || !lon_axis_host) return NSS_E_NULL;
+  if (nlat <= 0 || nlon <= 0) return NSS_E_BADARG;
+  cudaError_t err;
+  if (g_cloud.alt) {
+    cudaDeviceSynchronize();
+    cudaFree((void*)g_cloud.alt);
+    g_cloud = CloudMapView{nullptr, nullptr, nullptr, 0, 0};
+  }
+  const size_t nm = (size_t)nlat * nlon;
+  double* buf = nullptr;
+  if ((err = cudaMalloc(&buf, sizeof(double) * (nm + nlat + nlon))) != cudaSuccess)
+    return (int)err;
+  if ((err = cudaMemcpy(buf, alt_map_host, sizeof(double) * nm, cudaMemcpyHostToDevice)) !=
+          cudaSuccess ||
+      (err = cudaMemcpy(buf + nm, lat_axis_host, sizeof(double) * nlat,
+                        cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (err = cudaMemcpy(buf + nm + nlat, lon_axis_host, sizeof(double) * nlon,
+                        cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cudaFree(buf);
+    return (int)err;
+  }
+  g_cloud = CloudMapView{buf, buf + nm, buf + nm + nlat, nlat, nlon};
+  return 0;
+}
+
+extern "C" int nss_cloud_top_from_map(const double* lat, const double* lon, int64_t n,
+                                      double* cloud_top, void* stream) {
+  (void)lon;  // clouds.py:92 indexes the longitude axis with the latitude
+  if (n < 0) return NSS_E_BADARG;
+  if (n == 0) return 0;
+  if (!lat || !cloud_top || !g_cloud.alt) return NSS_E_NULL;
+  cloud_top_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(g_cloud, lat, n,
+                                                                       cloud_top);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int64_t nss_acceptance_workspace_bytes(int64_t batch) {
   if (batch <= 0) return 0;
-  return 9 * align256(batch * 8) + align256(batch) + align256((int64_t)MC_GRID * MC_NSUM * 8);
+  return 10 * align256(batch * 8) + align256(batch) + align256((int64_t)MC_GRID * MC_NSUM * 8);
 }
 
 extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64_t seed,
@@ -903,12 +992,13 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
                                   void* stream) {
   if (!p || !t || !out || !workspace) return NSS_E_NULL;
   if (n < 0 || batch <= 0) return NSS_E_BADARG;
+  if (p->has_cloud == 2 && !g_cloud.alt) return NSS_E_NULL;  // no map registered
   cudaStream_t s = (cudaStream_t)stream;
   char* w = (char*)workspace;
   FrontBufs b;
-  double** slots[9] = {&b.beta, &b.alt,   &b.shower, &b.fgeo, &b.ctrv,
-                       &b.pexit, &b.npe, &b.cth,    &b.uprof};
-  for (int k = 0; k < 9; ++k) {
+  double** slots[10] = {&b.beta,  &b.alt, &b.shower, &b.fgeo,  &b.ctrv,
+                        &b.pexit, &b.npe, &b.cth,    &b.uprof, &b.cloud};
+  for (int k = 0; k < 10; ++k) {
     *slots[k] = (double*)w;
     w += align256(batch * 8);
   }
@@ -920,10 +1010,11 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
   TabView tv = view_of(t);
   for (int64_t off = 0; off < n; off += batch) {
     const int64_t m = (n - off) < batch ? (n - off) : batch;
-    front_kernel<<<grid_for(m, 256), 256, 0, s>>>(*p, tv, seed, first_event + (uint64_t)off, m, b,
-                                                  flags);
+    front_kernel<<<grid_for(m, 256), 256, 0, s>>>(*p, tv, g_cloud, seed,
+                                                  first_event + (uint64_t)off, m, b, flags);
     int rc = nss_eas_optical(p, b.beta, b.alt, b.shower, b.mask,
-                             p->eas_profile == 2 ? b.uprof : nullptr, m, b.npe, b.cth, nullptr,
+                             p->eas_profile == 2 ? b.uprof : nullptr,
+                             p->has_cloud == 2 ? b.cloud : nullptr, m, b.npe, b.cth, nullptr,
                              nullptr, stats, stream);
     if (rc != 0) return rc;
     int grid = (int)((m + MC_BLOCK - 1) / MC_BLOCK < MC_GRID ? (m + MC_BLOCK - 1) / MC_BLOCK

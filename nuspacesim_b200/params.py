@@ -48,9 +48,10 @@ def params_from_config(config) -> _lib.NssParams:
             p.has_cloud = 0
             p.cloud_top = 0.0
     elif cid == "pressure_map":
-        raise NotImplementedError(
-            "PressureMapCloud is outside the accelerated path (SURVEY.md 8(f) rank 4)"
-        )
+        # one cloud top per event, looked up in the month's map (clouds.py:67-69, 85-107);
+        # CloudTopHeight.register() hands the map to the library
+        p.has_cloud = 2
+        p.cloud_top = 0.0
     else:
         # NoCloud: cloudf returns 0.0 km, below every step -> identical to no cloud
         p.has_cloud = 0

@@ -41,14 +41,31 @@ def _ensure_conex_on_device():
         _conex_uploaded = dev
 
 
-def cloud_scalar(cloudf):
-    """cloudf(lat, long) of the NoCloud/MonoCloud models is a constant (clouds.py:54-82)."""
+def cloud_args(cloudf, lat, long, n):
+    """-> (has_cloud, cloud_top, per-event device array or None) for ``cloudf(lat, long)``
+    (cphotang.py:644).  NoCloud/MonoCloud are constants (clouds.py:54-82); a
+    ``CloudTopHeight`` built from a PressureMapCloud is looked up on the GPU; any other
+    callable is evaluated on the host, vectorised over the events if it accepts arrays."""
     if cloudf is None:
-        return 0, 0.0
-    top = float(cloudf(0.0, 0.0))
-    if np.isneginf(top):
-        return 0, 0.0
-    return 1, top
+        return 0, 0.0, None
+    if getattr(cloudf, "per_event", False):
+        return 2, 0.0, cloudf.device_tops(lat, long)
+    if hasattr(cloudf, "per_event"):  # our own constant models
+        tops = cloudf(0.0, 0.0)
+    else:
+        la = _lib.to_host(lat) if _lib.is_device_array(lat) else np.asarray(lat, dtype=float)
+        lo = _lib.to_host(long) if _lib.is_device_array(long) else np.asarray(long, dtype=float)
+        try:
+            tops = np.asarray(cloudf(la, lo), dtype=np.float64)
+        except Exception:
+            tops = np.zeros(0)
+        if tops.ndim != 0 and tops.shape != (n,):
+            tops = np.array([float(cloudf(a, b)) for a, b in zip(la, lo)])
+    tops = np.asarray(tops, dtype=np.float64)
+    if tops.ndim == 0:
+        top = float(tops)
+        return (0, 0.0, None) if np.isneginf(top) else (1, top, None)
+    return 2, 0.0, _lib.to_device(tops)
 
 
 class CphotAng:
@@ -90,13 +107,14 @@ class CphotAng:
         dev = any(_lib.is_device_array(x) for x in (betaE, alt, Eshow100PeV))
         b, a, e = _lib.to_device(betaE), _lib.to_device(alt), _lib.to_device(Eshow100PeV)
         n = b.numel()
-        self.params.has_cloud, self.params.cloud_top = cloud_scalar(cloudf)
+        self.params.has_cloud, self.params.cloud_top, ctops = cloud_args(
+            cloudf, init_lat, init_long, n)
         d, c = _lib.empty(n), _lib.empty(n)
         up = self.profile_uniforms(n, u_profile)
         _lib.check(
             _lib.lib().nss_cphotang(C.byref(self.params), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e),
-                                    _lib.ptr(up), n, _lib.ptr(d), _lib.ptr(c), _lib.ptr(stats),
-                                    _lib.stream_ptr()),
+                                    _lib.ptr(up), _lib.ptr(ctops), n, _lib.ptr(d), _lib.ptr(c),
+                                    _lib.ptr(stats), _lib.stream_ptr()),
             "nss_cphotang",
         )
         return (d, c) if dev else (_lib.to_host(d), _lib.to_host(c))

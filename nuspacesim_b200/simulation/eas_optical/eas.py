@@ -14,7 +14,7 @@ import numpy as np
 from ... import _lib
 from ...params import params_from_config
 from ...utils import decorators
-from .cphotang import CphotAng, cloud_scalar
+from .cphotang import CphotAng, cloud_args
 
 __all__ = ["EAS"]
 
@@ -62,12 +62,13 @@ class EAS:
         b, a, e = _lib.to_device(beta), _lib.to_device(altDec), _lib.to_device(showerEnergy)
         n = b.numel()
         p = self.params
-        p.has_cloud, p.cloud_top = cloud_scalar(cloudf)
+        p.has_cloud, p.cloud_top, ctops = cloud_args(cloudf, init_lat, init_long, n)
         npe, cth = _lib.empty(n), _lib.empty(n)
         up = self.CphotAng.profile_uniforms(n, u_profile)
         _lib.check(
             _lib.lib().nss_eas_optical(C.byref(p), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e), None,
-                                       _lib.ptr(up), n, _lib.ptr(npe), _lib.ptr(cth), None, None,
+                                       _lib.ptr(up), _lib.ptr(ctops), n, _lib.ptr(npe),
+                                       _lib.ptr(cth), None, None,
                                        _lib.ptr(self.stats), _lib.stream_ptr()),
             "nss_eas_optical",
         )

@@ -178,6 +178,37 @@ def eas_gh():
     return out
 
 
+CLOUDMAP_TAGS = {"m01": 1, "m07": 7}
+
+
+def cloud_pressure_map(month):
+    """The shipped monthly cloud-top pressure map (tools/import_tables.py)."""
+    with np.load(os.path.join(ROOT, "nuspacesim_b200", "data", "cloud_maps",
+                              "nss_map_CloudTopPressure.v0.npz")) as z:
+        return z[f"m{month:02d}"]
+
+
+@pytest.fixture(scope="session")
+def eas_cloudmap():
+    """2 500 events of the reference's CphotAng.run under PressureMapCloud cloud tops
+    (tests/golden/make_golden_cloudmap.py), with the oracle's results and conditioning."""
+    from oracle import nss_oracle as O
+
+    G = np.load(os.path.join(GOLDEN, "eas_cloudmap.npz"))
+    nt = os.cpu_count() or 1
+    out = {"sweep_lat": G["sweep_lat"]}
+    for tag, month in CLOUDMAP_TAGS.items():
+        out["sweep_" + tag] = G["sweep_" + tag]
+        b, a, e = (G[f"{tag}_{k}"] for k in ("beta_rad", "altDec", "showerEnergy"))
+        tops = O.cloud_top_pressure_map(cloud_pressure_map(month), G[f"{tag}_lat"])
+        d0, c0, _ = O.cphotang(b, a, e, 525.0, tops, nthreads=nt)
+        out[tag] = dict(beta=b, alt=a, eshow=e, lat=G[f"{tag}_lat"], lon=G[f"{tag}_lon"],
+                        month=month, cloud_top=G[f"{tag}_cloud_top"], oracle_tops=tops,
+                        dphots=G[f"{tag}_dphots"], cang=G[f"{tag}_cang"], oracle_dphots=d0,
+                        oracle_cang=c0, sens=O.conditioning(b, a, e, 525.0, tops, nthreads=nt))
+    return out
+
+
 def check_engine_vs_reference(d, c, ref, what, median_tol=5e-5):
     """Stated float32 tolerance of the EAS engine against the reference on a large sample:
     median < 5e-5, 99 % < 3e-4, 99.9 % < 2e-3, every event < max(2.5e-3, 5 x conditioning);
@@ -185,9 +216,10 @@ def check_engine_vs_reference(d, c, ref, what, median_tol=5e-5):
     keep twice as many altitude steps and the oracle itself sits at 5.2e-5 there.)"""
     r = rel_err(d, ref["dphots"])
     assert np.array_equal(d == 0, ref["dphots"] == 0), what
-    assert np.median(r) < median_tol, (what, np.median(r))
-    assert np.percentile(r, 99) < 3e-4, (what, np.percentile(r, 99))
-    assert np.percentile(r, 99.9) < 2e-3, (what, np.percentile(r, 99.9))
+    live = np.asarray(ref["dphots"]) != 0  # clouded-out events agree exactly (0 == 0)
+    assert np.median(r[live]) < median_tol, (what, np.median(r[live]))
+    assert np.percentile(r[live], 99) < 3e-4, (what, np.percentile(r[live], 99))
+    assert np.percentile(r[live], 99.9) < 2e-3, (what, np.percentile(r[live], 99.9))
     bad = r > np.maximum(2.5e-3, 5 * ref["sens"])
     assert not bad.any(), (what, np.nonzero(bad)[0][:5], r[bad][:5])
     assert rel_err(c, ref["cang"]).max() < 5e-5, what

@@ -21,6 +21,7 @@ struct Ops1 {
 };
 }  // namespace
 
+// cloud_ev (optional): per-event cloud tops [km], overriding has_cloud / cloud_top
 // profile: 0 Greisen, 1 Gaisser-Hillas Parameterized, 2 Gaisser-Hillas Fluctuated with
 // gh_rows[i] = the (Nm, Xm, X0, p1, p2, p3) CONEX row of event i
 extern "C" int nss_emul_eas_profile(long long n, const double* beta, const double* alt,
@@ -28,7 +29,7 @@ extern "C" int nss_emul_eas_profile(long long n, const double* beta, const doubl
                                     double qe, double thr, int has_cloud, float cloud_top,
                                     double* numPEs, double* cosCh, double* dphots, double* cang,
                                     unsigned long long* stats6, int profile,
-                                    const double* gh_rows) {
+                                    const double* gh_rows, const double* cloud_ev) {
   nss::EasTables T;
   nss_eas_tables_init(&T);
   nss::EasParams P;
@@ -36,7 +37,7 @@ extern "C" int nss_emul_eas_profile(long long n, const double* beta, const doubl
   P.area = area;
   P.qe = qe;
   P.pe_threshold = thr;
-  P.has_cloud = has_cloud;
+  P.has_cloud = cloud_ev ? 2 : has_cloud;
   P.cloud_top = cloud_top;
   P.profile = profile;
   P.pad = 0;
@@ -46,13 +47,14 @@ extern "C" int nss_emul_eas_profile(long long n, const double* beta, const doubl
     if (!(alt[i] < 0.0 || alt[i] > 20.0)) {
       nss::EasPrep E;
       nss::EasAcc A;
+      const float ct = cloud_ev ? (float)cloud_ev[i] : cloud_top;
       nss::eas_prep(T, beta[i], alt[i], eshow[i], true, profile,
-                    profile == 2 ? gh_rows + 6 * i : nullptr, E);
+                    profile == 2 ? gh_rows + 6 * i : nullptr, ct, E);
       if (profile == 0)
-        nss::eas_walk<Ops1, false>(T, P, E, 0.0f, A, &st, true);
+        nss::eas_walk<Ops1, false>(T, P, E, 0.0f, E.cloud, A, &st, true);
       else
-        nss::eas_walk<Ops1, true>(T, P, E, 0.0f, A, &st, true);
-      nss::eas_finish(P, beta[i], alt[i], A, d, c);
+        nss::eas_walk<Ops1, true>(T, P, E, 0.0f, E.cloud, A, &st, true);
+      nss::eas_finish(P, beta[i], alt[i], A, E.cloud, d, c);
     }
     double npe, cc;
     nss::eas_tail(P, d, c, npe, cc);
@@ -74,7 +76,8 @@ extern "C" int nss_emul_eas(long long n, const double* beta, const double* alt,
                             double* numPEs, double* cosCh, double* dphots, double* cang,
                             unsigned long long* stats6) {
   return nss_emul_eas_profile(n, beta, alt, eshow, detector_altitude, area, qe, thr, has_cloud,
-                              cloud_top, numPEs, cosCh, dphots, cang, stats6, 0, nullptr);
+                              cloud_top, numPEs, cosCh, dphots, cang, stats6, 0, nullptr,
+                              nullptr);
 }
 
 // per-event prep record, for checking the column totals against a brute-force sum
@@ -82,7 +85,7 @@ extern "C" int nss_emul_prep(double beta, double alt, double eshow, float* out8,
   nss::EasTables T;
   nss_eas_tables_init(&T);
   nss::EasPrep E;
-  nss::eas_prep(T, beta, alt, eshow, true, 0, nullptr, E);
+  nss::eas_prep(T, beta, alt, eshow, true, 0, nullptr, 0.0f, E);
   out8[0] = E.R0; out8[1] = E.q; out8[2] = E.alt; out8[3] = E.Ldet;
   out8[4] = E.Gtot; out8[5] = E.ozA[E.seg0]; out8[6] = E.gb; out8[7] = E.alpha;
   out2[0] = E.n_raw; out2[1] = E.Ieang;

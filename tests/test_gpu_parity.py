@@ -15,9 +15,9 @@ Tolerances (stated):
 import numpy as np
 import pytest
 
-from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, GH_PROFILES, GH_TAGS, PIPE_TAGS, TAU_TABLES,
-                      check_engine_vs_reference, conex_rows, load_tables, make_config,
-                      philox_uniforms, rel_err)
+from conftest import (CLOUDMAP_TAGS, EAS_LARGE_TAGS, GEOM_TAGS, GH_PROFILES, GH_TAGS, PIPE_TAGS,
+                      TAU_TABLES, check_engine_vs_reference, cloud_pressure_map, conex_rows,
+                      load_tables, make_config, philox_uniforms, rel_err)
 from oracle import nss_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -514,3 +514,60 @@ def test_gaisser_hillas_fluctuated_needs_uniforms(nss):
     assert rc == -2  # null u_profile
     with pytest.raises(ValueError):
         nss.CphotAng(525.0, "Linsley")
+
+
+# ------------------------------------------------------------------ PressureMapCloud
+
+
+@pytest.mark.parametrize("tag", sorted(CLOUDMAP_TAGS))
+def test_pressure_map_cloud_engine(nss, eas_cloudmap, tag):
+    """nss_cloud_top_from_map equals the reference's cloudf bit for bit; CphotAng with the
+    PressureMapCloud CloudTopHeight clouds out the same events as the reference and agrees on
+    the others within the stated tolerance."""
+    from nuspacesim_b200.config import PressureMapCloud
+    from nuspacesim_b200.simulation.atmosphere.clouds import CloudTopHeight
+
+    cfg = make_config()
+    cfg.simulation.cloud_model = PressureMapCloud(month=CLOUDMAP_TAGS[tag])
+    ct = CloudTopHeight(cfg)
+    tops = ct.device_tops(eas_cloudmap["sweep_lat"]).cpu().numpy()
+    assert np.array_equal(tops, eas_cloudmap["sweep_" + tag])
+    ref = eas_cloudmap[tag]
+    cp = nss.CphotAng(525.0, "Greisen")
+    d, c = cp(ref["beta"], ref["alt"], ref["eshow"], ref["lat"], ref["lon"], ct)
+    check_engine_vs_reference(np.asarray(d), np.asarray(c), ref, f"gpu/{tag}")
+    # a plain Python callable (evaluated on the host, per event) gives the same answer
+    d2, _ = cp(ref["beta"][:64], ref["alt"][:64], ref["eshow"][:64], ref["lat"][:64],
+               ref["lon"][:64], lambda la, lo: float(ct(la, lo)))
+    assert np.array_equal(np.asarray(d2), np.asarray(d)[:64])
+
+
+def test_pressure_map_cloud_compute_and_acceptance(nss, tables_v3):
+    """compute() and the fused acceptance mode under PressureMapCloud: identical events
+    (the cloud top comes from the ground-spot latitude of each trajectory,
+    compute.py:214-216), both equal to the oracle fed the identical uniforms."""
+    from nuspacesim_b200.config import PressureMapCloud
+
+    seed, n = 21, 6000
+    cfg = make_config(n=n, loge=9.0)
+    cfg.simulation.cloud_model = PressureMapCloud(month=1)
+    r = nss.AcceptanceRunner(cfg, batch=2048)
+    r.enqueue(seed, 0, n)
+    got = r.finalize(r.sums())
+    sim = nss.compute(cfg, seed=seed)
+    assert sim.meta["ONEVPASS"][0] == got[2]
+    np.testing.assert_allclose(sim.meta["OMCINT"][0], got[0], rtol=1e-12)
+    u4, us, ut, ud, _ = philox_uniforms(seed, 0, n)
+    p = O.OracleParams(log_nu_energy=9.0, cloud_map=cloud_pressure_map(1))
+    mc, cols, t, _ = O.run_path(p, tables_v3, u4, us, ut, ud, nthreads=4)
+    assert np.array_equal(sim["numPEs"] == 0, cols["numPEs"] == 0)
+    live = cols["numPEs"] > 0
+    rd = rel_err(sim["numPEs"][live], cols["numPEs"][live])
+    assert np.median(rd) < 1e-5 and rd.max() < 2.5e-3, rd.max()
+    # the clouds matter for this configuration
+    clear = nss.compute(make_config(n=n, loge=9.0), seed=seed)
+    assert np.count_nonzero(clear["numPEs"] > 0) > np.count_nonzero(live)
+    near = np.abs(cols["numPEs"] / 10.0 - 1) < 2.5e-3
+    if not near.any():
+        assert got[2] == mc[2]
+        np.testing.assert_allclose(got[0], mc[0], rtol=1e-11)

@@ -10,8 +10,9 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import (EAS_LARGE_TAGS, GH_PROFILES, GH_TAGS, ROOT, check_engine_vs_reference,
-                      load_tables, make_config, philox_uniforms, rel_err)
+from conftest import (CLOUDMAP_TAGS, EAS_LARGE_TAGS, GH_PROFILES, GH_TAGS, ROOT,
+                      check_engine_vs_reference, load_tables, make_config, philox_uniforms,
+                      rel_err)
 from oracle import nss_oracle as O
 
 
@@ -56,14 +57,18 @@ def test_null_and_bad_arguments_are_rejected_without_gpu():
     assert L.nss_geom_throw_u(ctypes.byref(p), None, 5, None, None) == -2
     assert L.nss_alt_dec(None, None, None, None, -1, None, None, None) == -1
     assert L.nss_alt_dec(None, None, None, None, 0, None, None, None) == 0  # empty input
-    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, None, 0, None, None, None,
-                             None, None, None) == 0
-    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, None, 3, None, None, None,
-                             None, None, None) == -2
+    eas_args = lambda n: (ctypes.byref(p), None, None, None, None, None, None, n, None, None,
+                          None, None, None, None)
+    assert L.nss_eas_optical(*eas_args(0)) == 0
+    assert L.nss_eas_optical(*eas_args(3)) == -2
     p.eas_profile = 7  # unknown longitudinal profile
-    assert L.nss_eas_optical(ctypes.byref(p), None, None, None, None, None, 3, None, None, None,
-                             None, None, None) == -1
+    assert L.nss_eas_optical(*eas_args(3)) == -1
     p.eas_profile = 0
+    p.has_cloud = 3  # unknown cloud model
+    assert L.nss_eas_optical(*eas_args(3)) == -1
+    p.has_cloud = 0
+    assert L.nss_cloud_set_altitude_map(None, 3, 3, None, None) == -2
+    assert L.nss_cloud_top_from_map(None, None, 0, None, None) == 0
     assert L.nss_eas_set_conex_table(None, 10) == -2
     h = ctypes.c_void_p()
     a = (ctypes.c_double * 4)()
@@ -238,17 +243,19 @@ def emul():
     L = ctypes.CDLL(lib)
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
-    def run(beta, alt, es, det=525.0, top=None, profile=0, rows=None):
+    def run(beta, alt, es, det=525.0, top=None, profile=0, rows=None, cloud_ev=None):
         beta, alt, es = (np.ascontiguousarray(x, float) for x in (beta, alt, es))
         n = beta.size
         npe, cc, d, c = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
         st = (ctypes.c_ulonglong * 6)()
         rows = None if rows is None else np.ascontiguousarray(rows, float)
+        cloud_ev = None if cloud_ev is None else np.ascontiguousarray(cloud_ev, float)
         L.nss_emul_eas_profile(
             ctypes.c_longlong(n), dp(beta), dp(alt), dp(es), ctypes.c_double(det),
             ctypes.c_double(2.5), ctypes.c_double(0.2), ctypes.c_double(10.0),
             ctypes.c_int(top is not None), ctypes.c_float(top or 0.0), dp(npe), dp(cc), dp(d),
-            dp(c), st, ctypes.c_int(profile), None if rows is None else dp(rows))
+            dp(c), st, ctypes.c_int(profile), None if rows is None else dp(rows),
+            None if cloud_ev is None else dp(cloud_ev))
         return npe, cc, d, c, list(st)
 
     return run
@@ -399,6 +406,36 @@ def test_kernel_arithmetic_on_host_gaisser_hillas(emul, eas_gh, tag, short):
     check_engine_vs_reference(d, c, ref, f"host-emul/{tag}/{short}",
                               median_tol=7e-5 if short == "ghf" else 5e-5)
     assert np.median(rel_err(d, ref["oracle_dphots"])) < 1e-5
+
+
+@pytest.mark.parametrize("tag", sorted(CLOUDMAP_TAGS))
+def test_pressure_map_cloud_host_side(emul, eas_cloudmap, tag):
+    """CloudTopHeight for a PressureMapCloud config evaluated on the host equals the
+    reference's cloudf bit for bit; the kernel arithmetic (host build) under per-event cloud
+    tops clouds out the same events and agrees within the stated tolerance."""
+    from nuspacesim_b200.config import PressureMapCloud
+    from nuspacesim_b200.params import params_from_config
+    from nuspacesim_b200.simulation.atmosphere.clouds import CloudTopHeight
+
+    cfg = make_config()
+    cfg.simulation.cloud_model = PressureMapCloud(month=CLOUDMAP_TAGS[tag])
+    assert params_from_config(cfg).has_cloud == 2
+    ct = CloudTopHeight(cfg)
+    assert ct.per_event
+    assert np.array_equal(ct(eas_cloudmap["sweep_lat"], 0.0), eas_cloudmap["sweep_" + tag])
+    assert float(ct(0.25, -1.0)) == float(ct(np.array([0.25]), np.array([2.0]))[0])
+    ref = eas_cloudmap[tag]
+    _, _, d, c, _ = emul(ref["beta"], ref["alt"], ref["eshow"], 525.0,
+                         cloud_ev=ct(ref["lat"], ref["lon"]))
+    check_engine_vs_reference(d, c, ref, f"host-emul/{tag}")
+    with pytest.raises(ValueError):
+        CloudTopHeight(make_config_with_cloud(PressureMapCloud(month=13)))
+
+
+def make_config_with_cloud(model):
+    cfg = make_config()
+    cfg.simulation.cloud_model = model
+    return cfg
 
 
 @pytest.mark.parametrize("tag", EAS_LARGE_TAGS)

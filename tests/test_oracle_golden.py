@@ -4,8 +4,9 @@ the reference's own known-answer vectors.  CPU only."""
 import numpy as np
 import pytest
 
-from conftest import (EAS_LARGE_TAGS, GEOM_TAGS, GH_PROFILES, GH_TAGS, PIPE_TAGS, TAU_TABLES,
-                      check_engine_vs_reference, conex_rows, load_tables, rel_err)
+from conftest import (CLOUDMAP_TAGS, EAS_LARGE_TAGS, GEOM_TAGS, GH_PROFILES, GH_TAGS, PIPE_TAGS,
+                      TAU_TABLES, check_engine_vs_reference, cloud_pressure_map, conex_rows,
+                      load_tables, rel_err)
 from oracle import nss_oracle as O
 
 # Known-answer vectors copied from the reference's test data
@@ -174,6 +175,35 @@ def test_conex_table_is_the_reference_table():
            "dumpGH_conex_pi_E17_95deg_0km_eposlhc_1394249052_211.dat")
     if os.path.exists(src):
         assert np.array_equal(T, np.loadtxt(src, usecols=(4, 5, 6, 7, 8, 9)))
+
+
+@pytest.mark.parametrize("tag", sorted(CLOUDMAP_TAGS))
+def test_pressure_map_cloud(eas_cloudmap, tag):
+    """PressureMapCloud (clouds.py:85-107): the lookup + standard-atmosphere conversion is
+    bit-identical to the reference's cloudf on a latitude sweep and on the event sample; the
+    engine under per-event cloud tops agrees with the reference within the stated tolerance
+    and clouds out exactly the same events."""
+    month = CLOUDMAP_TAGS[tag]
+    m = cloud_pressure_map(month)
+    assert np.array_equal(O.cloud_top_pressure_map(m, eas_cloudmap["sweep_lat"]),
+                          eas_cloudmap["sweep_" + tag])
+    ref = eas_cloudmap[tag]
+    assert np.array_equal(ref["oracle_tops"], ref["cloud_top"])
+    assert 0 < np.count_nonzero(ref["dphots"] == 0) < len(ref["dphots"])
+    check_engine_vs_reference(ref["oracle_dphots"], ref["oracle_cang"], ref, f"oracle/{tag}")
+
+
+def test_cloud_maps_are_the_reference_maps():
+    import os
+
+    for month in (1, 6, 12):
+        m = cloud_pressure_map(month)
+        assert m.shape == (361, 576) and m.dtype == np.float32
+        src = f"/root/reference/src/nuspacesim/data/cloud_maps/nss_map_CloudTopPressure_{month:02d}.v0.fits"
+        if os.path.exists(src):
+            raw = open(src, "rb").read()
+            want = np.frombuffer(raw[2880:2880 + 361 * 576 * 4], dtype=">f4").reshape(361, 576)
+            assert np.array_equal(m, want)
 
 
 @pytest.mark.parametrize("tag", PIPE_TAGS)

@@ -50,6 +50,27 @@ def import_conex(src):
     print("CONEX_table", tab.shape)
 
 
+def import_cloud_maps(src):
+    """The twelve monthly cloud-top pressure maps (primary HDU, 361 x 576 float32, Pa) of
+    PressureMapCloud (atmosphere/clouds.py:99-107), gathered into one compressed .npz with keys
+    m01..m12 (the FITS files hold ~240 distinct pressure levels each and deflate 3:1)."""
+    dst = os.path.join(ROOT, "nuspacesim_b200", "data", "cloud_maps")
+    os.makedirs(dst, exist_ok=True)
+    out = {}
+    for month in range(1, 13):
+        raw = open(os.path.join(src, "cloud_maps",
+                                f"nss_map_CloudTopPressure_{month:02d}.v0.fits"), "rb").read()
+        cards = {raw[i:i + 8].decode().strip(): raw[i + 10:i + 80].decode().split("/")[0].strip()
+                 for i in range(0, 2880, 80)}
+        assert cards["BITPIX"] == "-32" and cards["NAXIS"] == "2", cards
+        n1, n2 = int(cards["NAXIS1"]), int(cards["NAXIS2"])
+        out[f"m{month:02d}"] = np.frombuffer(raw[2880:2880 + 4 * n1 * n2], dtype=">f4").reshape(
+            n2, n1).astype(np.float32)
+    np.savez_compressed(os.path.join(dst, "nss_map_CloudTopPressure.v0.npz"), **out)
+    print("cloud_maps", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main(sys.argv[1])
     import_conex(sys.argv[1])
+    import_cloud_maps(sys.argv[1])
