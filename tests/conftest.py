@@ -219,7 +219,8 @@ def check_engine_vs_reference(d, c, ref, what, median_tol=5e-5):
     live = np.asarray(ref["dphots"]) != 0  # clouded-out events agree exactly (0 == 0)
     assert np.median(r[live]) < median_tol, (what, np.median(r[live]))
     assert np.percentile(r[live], 99) < 3e-4, (what, np.percentile(r[live], 99))
-    assert np.percentile(r[live], 99.9) < 2e-3, (what, np.percentile(r[live], 99.9))
+    if live.sum() >= 3000:  # below that the 99.9th percentile is just the largest event
+        assert np.percentile(r[live], 99.9) < 2e-3, (what, np.percentile(r[live], 99.9))
     bad = r > np.maximum(2.5e-3, 5 * ref["sens"])
     assert not bad.any(), (what, np.nonzero(bad)[0][:5], r[bad][:5])
     assert rel_err(c, ref["cang"]).max() < 5e-5, what

@@ -509,9 +509,13 @@ def test_gaisser_hillas_fluctuated_needs_uniforms(nss):
     p = _lib.NssParams()
     p.eas_profile = 2
     x = _lib.to_device(np.ones(4))
-    rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None, 4,
-                                 _lib.ptr(x), _lib.ptr(x), None, None)
+    rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, None)
     assert rc == -2  # null u_profile
+    p.eas_profile, p.has_cloud = 0, 2
+    rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, None)
+    assert rc == -2  # per-event cloud model without cloud tops
     with pytest.raises(ValueError):
         nss.CphotAng(525.0, "Linsley")
 
