@@ -539,7 +539,7 @@ def test_pressure_map_cloud_engine(nss, eas_cloudmap, tag):
     ref = eas_cloudmap[tag]
     cp = nss.CphotAng(525.0, "Greisen")
     d, c = cp(ref["beta"], ref["alt"], ref["eshow"], ref["lat"], ref["lon"], ct)
-    check_engine_vs_reference(np.asarray(d), np.asarray(c), ref, f"gpu/{tag}")
+    check_engine_vs_reference(np.asarray(d), np.asarray(c), ref, f"gpu/{tag}", cang_tol=1.5e-4)
     # a plain Python callable (evaluated on the host, per event) gives the same answer
     d2, _ = cp(ref["beta"][:64], ref["alt"][:64], ref["eshow"][:64], ref["lat"][:64],
                ref["lon"][:64], lambda la, lo: float(ct(la, lo)))
