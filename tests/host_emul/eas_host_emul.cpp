@@ -91,3 +91,14 @@ extern "C" int nss_emul_prep(double beta, double alt, double eshow, float* out8,
   out2[0] = E.n_raw; out2[1] = E.Ieang;
   return 0;
 }
+
+// ozone segment index of n altitudes: reference loop and the walk's arithmetic shortcut
+extern "C" int nss_emul_ozone_segments(long long n, const float* z, int* slow, int* fast) {
+  nss::EasTables T;
+  nss_eas_tables_init(&T);
+  for (long long i = 0; i < n; ++i) {
+    slow[i] = nss::ozone_segment(T, z[i]);
+    fast[i] = nss::ozone_segment_fast(T, z[i]);
+  }
+  return 0;
+}

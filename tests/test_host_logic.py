@@ -351,6 +351,22 @@ def test_prep_column_totals_vs_brute_force():
         assert abs(f8[5] - Z) / Z < 2e-5, (b, a, f8[5], Z)
 
 
+def test_ozone_segment_shortcut_is_exact(emul):
+    """ozone_segment_fast (one multiply, one floor, one comparison) against the ten-comparison
+    definition for a dense float32 altitude grid and one ulp either side of every knot."""
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "host_emul", "libeas_host_emul.so"))
+    knots = np.array([5.35, 10.2, 14.75, 19.15, 23.55, 28.1, 32.8, 37.7, 42.85, 48.25], np.float32)
+    z = np.concatenate([np.linspace(-2, 70, 3_000_001).astype(np.float32), knots,
+                        np.nextafter(knots, np.float32(0)), np.nextafter(knots, np.float32(99))])
+    slow, fast = np.zeros(z.size, np.int32), np.zeros(z.size, np.int32)
+    L.nss_emul_ozone_segments(ctypes.c_longlong(z.size),
+                              z.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                              slow.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                              fast.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert np.array_equal(slow, fast)
+    assert slow.min() == 0 and slow.max() == 10
+
+
 def test_nssgrid_fits_layout_roundtrip(tmp_path):
     """NssGrid FITS layout (grid.py:286-311): primary image + one BinTable HDU per axis."""
     from nuspacesim_b200.utils import fits_min
