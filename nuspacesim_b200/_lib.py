@@ -212,6 +212,13 @@ def to_device_prefetch(x, dtype="float64"):
     return t, ev
 
 
+def h2d_synchronize():
+    """Wait for every prefetch started by `to_device_prefetch` (the caller may reuse or free
+    its pinned host buffers afterwards)."""
+    if _H2D_STREAM is not None:
+        _H2D_STREAM.synchronize()
+
+
 def empty(n, dtype="float64"):
     torch = torch_cuda()
     return torch.empty(int(n), dtype=getattr(torch, dtype), device="cuda")

@@ -39,9 +39,12 @@ def compute(config, verbose: bool = False, output_file: str = None, to_plot: lis
     ``u_tau``, ``u_dec``, ``u_profile`` (N,) indexed by thrown event, for shared-input
     validation.
     """
-    with _lib.deferred_host_copies() as sink:
-        return _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms,
-                        sink)
+    try:
+        with _lib.deferred_host_copies() as sink:
+            return _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms,
+                            sink)
+    finally:
+        _lib.h2d_synchronize()  # the caller's pinned uniforms are free to be reused
 
 
 class StagedWriter:

@@ -6,6 +6,8 @@ import nuspacesim_b200 as nss
 
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 20
 cfg = nss.NssConfig()
+if len(sys.argv) > 2:  # longitudinal profile, e.g. "Gaisser-Hillas Fluctuated"
+    cfg.simulation.eas_long_profile = sys.argv[2]
 r = nss.AcceptanceRunner(cfg, batch=1 << 20, collect_stats=True)
 r.enqueue(1234, 0, 1 << 16)
 torch.cuda.synchronize()
