@@ -314,22 +314,34 @@ def main():
         sim = None
         sync_all()
         k_e2e = max(1, min(args.steps, 3))
-        n_warm = 2  # the second warm-up lets the pinned-host cache recycle the first table
+        # warm-ups: the first two calls pin ~2.4 GB of host memory for two generations of the
+        # results table (cudaHostAlloc, ~1 s each); from the third on the pinned-host cache
+        # recycles them
+        n_warm = int(os.environ.get("NSS_BENCH_E2E_WARMUP", "3"))
+        step_s = []
         for i in range(n_warm + k_e2e):
             if i == n_warm:
                 sync_all()
                 t0 = time.perf_counter()
+            t1 = time.perf_counter()
             sim = nss.compute(cfg, uniforms=pinned)
             d2h = sum(np.asarray(sim[c]).nbytes for c in sim.colnames) + 4 * 8
+            step_s.append(time.perf_counter() - t1)
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dt_local = time.perf_counter() - t0
+        dt = torch.tensor([dt_local], dtype=torch.float64, device="cuda")
+        per_rank = [dt_local]
         if world > 1:
+            gathered = [torch.zeros_like(dt) for _ in range(world)]
+            dist.all_gather(gathered, dt)
+            per_rank = [float(g.item()) for g in gathered]
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = dict(value=n * world * k_e2e / float(dt.item()), unit=UNIT,
                    h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=k_e2e,
                    api="nuspacesim_b200.compute(config, uniforms=<pinned host arrays>) -> "
                        "15-column table + OMCINT meta on the host",
-                   mcint=float(sim.meta["OMCINT"][0]), n_valid=len(sim))
+                   mcint=float(sim.meta["OMCINT"][0]), n_valid=len(sim),
+                   per_rank_s=per_rank, rank0_call_s=step_s)
 
     if rank == 0:
         line = dict(

@@ -212,6 +212,29 @@ def to_device_prefetch(x, dtype="float64"):
     return t, ev
 
 
+def rows_to_device_prefetch(x, lo, hi, dtype="float64"):
+    """Columns [lo, hi) of a 2-D host array as a contiguous CUDA tensor (rows copied one by one
+    so a pinned source needs no host-side repacking) -> (tensor, event or None)."""
+    global _H2D_STREAM
+    torch = torch_cuda()
+    td = getattr(torch, dtype)
+    pinned = (hasattr(x, "is_pinned") and not x.is_cuda and x.is_pinned() and x.dtype == td)
+    if not pinned:
+        if hasattr(x, "is_cuda"):
+            return x[:, lo:hi].to(device="cuda", dtype=td).contiguous(), None
+        return to_device(np.ascontiguousarray(np.asarray(x)[:, lo:hi], dtype=dtype)), None
+    if _H2D_STREAM is None:
+        _H2D_STREAM = torch.cuda.Stream()
+    with torch.cuda.stream(_H2D_STREAM):
+        t = torch.empty((x.shape[0], hi - lo), dtype=td, device="cuda")
+        for r in range(x.shape[0]):
+            t[r].copy_(x[r, lo:hi], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(_H2D_STREAM)
+    t.record_stream(torch.cuda.current_stream())
+    return t, ev
+
+
 def h2d_synchronize():
     """Wait for every prefetch started by `to_device_prefetch` (the caller may reuse or free
     its pinned host buffers afterwards)."""
@@ -258,6 +281,20 @@ class _HostSink:
         if not self.deferred:
             self.stream.synchronize()
         return out.numpy()  # the array keeps the pinned tensor alive
+
+    def copy_into(self, dst_pinned, t):
+        """Asynchronous device -> host copy of `t` into a slice of a pinned host tensor, on the
+        copy stream, after everything enqueued so far on the current stream."""
+        torch = torch_cuda()
+        t = t.detach().contiguous()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            dst_pinned.copy_(t, non_blocking=True)
+        t.record_stream(self.stream)
+        if not self.deferred:
+            self.stream.synchronize()
 
     def defer_check(self, flags, raiser):
         """Error flags of a kernel are read back with everything else at the end of the

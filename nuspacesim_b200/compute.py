@@ -30,17 +30,41 @@ from .simulation.taus.taus import Taus
 __all__ = ["compute", "run_acceptance"]
 
 
+#: thrown events per slice of compute()'s pipelined path (the acceptance mode's batch size)
+SLICE_EVENTS = 1 << 21
+
+COLUMN_GROUPS = (
+    ("beta_rad", "theta_rad", "path_len"), ("init_lat", "init_lon"), ("log_e_nu",),
+    ("tauBeta", "tauLorentz", "tauEnergy", "showerEnergy", "tauExitProb"),
+    ("altDec", "lenDec"), ("numPEs", "costhetaChEff"),
+)
+
+
 def compute(config, verbose: bool = False, output_file: str = None, to_plot: list = [],
-            write_stages: bool = False, seed: int = 0, uniforms: dict = None):
+            write_stages: bool = False, seed: int = 0, uniforms: dict = None,
+            slice_events: int = None):
     """Simulate an upward going shower (compute.py:73-298, optical branch).
 
     Extensions: ``seed`` keys the Philox streams (the reference uses the global unseeded
     NumPy state); ``uniforms`` may hold pre-sampled arrays ``u4`` (4, N), ``u_spec``,
     ``u_tau``, ``u_dec``, ``u_profile`` (N,) indexed by thrown event, for shared-input
-    validation.
+    validation.  Large runs are pipelined in slices of ``slice_events`` thrown events
+    (default ``SLICE_EVENTS``; 0 disables): the stage sequence runs slice by slice so that the
+    upload of the next slice's uniforms and the download of the previous slice's columns hide
+    behind the EAS kernel.  Per-event results do not depend on the slicing; staged writes and
+    plots use the unsliced path (they need whole columns after every stage).
     """
+    n_thrown = config.simulation.thrown_events
+    if uniforms and "u4" in uniforms:
+        n_thrown = int(uniforms["u4"].shape[1]) if getattr(uniforms["u4"], "ndim", 0) == 2 else 0
+    step = SLICE_EVENTS if slice_events is None else int(slice_events)
+    sliced = (step > 0 and n_thrown >= 2 * step and not write_stages and not to_plot
+              and config.simulation.mode != "Target" and config.detector.optical.enable)
     try:
         with _lib.deferred_host_copies() as sink:
+            if sliced:
+                return _compute_sliced(config, verbose, output_file, seed, uniforms, sink,
+                                       int(n_thrown), step)
             return _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms,
                             sink)
     finally:
@@ -162,6 +186,121 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
 
     if output_file is not None and not write_stages:
         sink.synchronize()
+        sim.write(output_file, format="fits", overwrite=True)
+    return sim
+
+
+def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown, step):
+    """compute() for large N: the same stage objects, called per slice of thrown events.
+
+    Slice k owns thrown events [lo, hi); valid events keep their thrown order, so the result
+    columns are the concatenation of the slices' columns.  Every slice's uniforms are put on
+    the upload stream up front; its columns go to their rows of full-length pinned host
+    arrays on the copy stream while the next slice computes; the five acceptance sums per
+    slice stay on the device until the end and are merged exactly (Chan's update for the sum
+    of squared deviations)."""
+
+    def logv(*args):
+        if verbose:
+            print(*args)
+
+    torch = _lib.torch_cuda()
+    sim = results_table.init(config)
+    cloud = CloudTopHeight(config)
+    spec = Spectra(config, seed=seed)
+    tau = Taus(config, seed=seed)
+    eas = EAS(config, seed=seed)
+    U = uniforms or {}
+    bounds = [(lo, min(lo + step, n_thrown)) for lo in range(0, n_thrown, step)]
+    logv(f"Running NuSpaceSim with Energy Spectrum ({config.simulation.spectrum})")
+    logv(f"Computing {n_thrown} thrown events in {len(bounds)} pipelined slices.")
+
+    # uploads of every slice, in consumption order, on the side stream
+    pre = []
+    for lo, hi in bounds:
+        d = {}
+        if "u4" in U:
+            d["u4"] = _lib.rows_to_device_prefetch(U["u4"], lo, hi)
+        for name in ("u_spec", "u_tau", "u_dec", "u_profile"):
+            if name in U:
+                d[name] = _lib.to_device_prefetch(U[name][lo:hi])
+        pre.append(d)
+
+    names = [n for g in COLUMN_GROUPS for n in g]
+    host = {n: torch.empty(n_thrown, dtype=torch.float64, pin_memory=True) for n in names}
+    WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2, "u_profile": 3}
+    sums, off = [], 0
+    thr = config.detector.optical.photo_electron_threshold
+    mc_spec_norm = spec_weights_sum = 1.0
+    for (lo, hi), d in zip(bounds, pre):
+        geom = RegionGeom(config, seed=seed)
+        geom.first_event = lo
+        thrown = hi - lo
+        if "u4" in d:
+            thrown, ev = d["u4"]
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+        beta_tr, theta, path_len = geom(thrown, device=True)
+        nv = int(beta_tr.numel())
+        if nv == 0:
+            continue
+
+        def valid_u(name):
+            if name in d:
+                full, ev = d[name]
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                return geom.compact(full)
+            return geom.event_uniforms(WHICH[name]) if "u4" not in U else None
+
+        cols = dict(beta_rad=beta_tr, theta_rad=theta, path_len=path_len)
+        cols["init_lat"], cols["init_lon"] = geom.find_lat_long_along_traj(
+            torch.zeros_like(beta_tr), device=True)
+        cols["log_e_nu"], mc_spec_norm, spec_weights_sum = spec(
+            nv, device=True, u=valid_u("u_spec"))
+        (cols["tauBeta"], cols["tauLorentz"], cols["tauEnergy"], cols["showerEnergy"],
+         cols["tauExitProb"]) = tau(beta_tr, cols["log_e_nu"], u=valid_u("u_tau"))
+        cols["altDec"], cols["lenDec"] = eas.altDec(beta_tr, cols["tauBeta"], cols["tauLorentz"],
+                                                    valid_u("u_dec"))
+        front = [n for n in names if n not in ("numPEs", "costhetaChEff")]
+        for n in front:  # these travel while the EAS kernel runs
+            sink.copy_into(host[n][off:off + nv], cols[n])
+        u_prof = valid_u("u_profile") if eas.params.eas_profile == 2 else None
+        cols["numPEs"], cols["costhetaChEff"] = eas(
+            beta_tr, cols["altDec"], cols["showerEnergy"], cols["init_lat"], cols["init_lon"],
+            cloudf=cloud, u_profile=u_prof)
+        for n in ("numPEs", "costhetaChEff"):
+            sink.copy_into(host[n][off:off + nv], cols[n])
+        sums.append(geom.mcintegral(cols["numPEs"], cols["costhetaChEff"], cols["tauExitProb"],
+                                    thr, mc_spec_norm, spec_weights_sum, device_sums=True))
+        off += nv
+
+    logv(f"\tThrew {n_thrown} neutrinos. {off} were valid.")
+    if off == 0:
+        print("\tWARNING: No valid events thrown! Exiting early! Check geometry!")
+        return sim
+    S = torch.stack(sums).cpu().numpy()  # (slices, 8): sum geo, sum f, M2, n_pass, n_valid, ...
+    sink.synchronize()
+    for group in COLUMN_GROUPS:
+        sim.add_columns([host[n].numpy()[:off] for n in group], names=group)
+    mcnorm = float(RegionGeom(config, seed=seed).mcnorm)
+    n_valid = S[:, 4].sum()
+    mean = S[:, 1].sum() / n_valid
+    with np.errstate(invalid="ignore", divide="ignore"):
+        m2 = float((S[:, 2] + S[:, 4] * (S[:, 1] / S[:, 4] - mean) ** 2).sum())
+        mcunc = float(np.sqrt(m2 / (n_valid - 1.0) / n_thrown) * mcnorm)
+    mcint = float(S[:, 1].sum() * mcnorm / n_thrown)
+    mcintgeo = float(S[:, 0].sum() * mcnorm / n_thrown)
+    passEV = int(S[:, 3].sum())
+    sim.meta["OMCINT"] = (mcint, "Optical MonteCarlo Integral")
+    sim.meta["OMCINTGO"] = (mcintgeo, "Optical MonteCarlo Integral, GEO Only")
+    sim.meta["ONEVPASS"] = (passEV, "Optical Number of Passing Events")
+    sim.meta["OMCINTUN"] = (mcunc, "Stat unc of MonteCarlo Integral")
+    logv(f"\tMonte Carlo Integral [Optical]: {mcint}")
+    logv(f"\tMonte Carlo Integral, GEO Only [Optical]: {mcintgeo}")
+    logv(f"\tNumber of Passing Events [Optical]: {passEV}")
+    logv(f"\tStat uncert of MC Integral [Optical]: {mcunc}")
+    if output_file is not None:
         sim.write(output_file, format="fits", overwrite=True)
     return sim
 

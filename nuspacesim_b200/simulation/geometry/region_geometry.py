@@ -258,5 +258,9 @@ class RegionGeom:
                 float(spec_weights_sum), _lib.ptr(out), _lib.ptr(ws), _lib.stream_ptr()),
             "nss_mcintegral",
         )
+        if kwargs.get("device_sums", False):
+            # extension (compute()'s sliced pipeline): the raw device sums {sum f_geo, sum f,
+            # sum (f - mean)^2, n_pass, n_valid, ...} without a host synchronisation
+            return out
         o = _lib.to_host(out)
         return float(o[5]), float(o[6]), int(o[3]), float(o[7])

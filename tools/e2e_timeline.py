@@ -14,7 +14,10 @@ for name, shape in (("u4", (4, n)), ("u_tau", (n,)), ("u_dec", (n,))):
     t = torch.empty(shape, dtype=torch.float64).pin_memory()
     t.numpy()[...] = rng.random(shape)
     pinned[name] = t
-for i in range(3):
+n_warm = int(os.environ.get("NSS_TL_WARM", "3"))   # un-profiled calls before the profiled one
+n_after = int(os.environ.get("NSS_TL_AFTER", "0"))  # ... and after it (keeps the load up when
+# several GPUs are profiled side by side: CUDA_VISIBLE_DEVICES=i python tools/e2e_timeline.py &)
+for i in range(n_warm):
     t0 = time.perf_counter(); sim = nss.compute(cfg, uniforms=pinned); torch.cuda.synchronize()
     print("warm", i, time.perf_counter() - t0, flush=True)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
@@ -23,6 +26,9 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 print("compute s", dt, "events/s", n / dt)
+for i in range(n_after):
+    t0 = time.perf_counter(); sim2 = nss.compute(cfg, uniforms=pinned); torch.cuda.synchronize()
+    print("after", i, time.perf_counter() - t0, flush=True)
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
 t_first = ev[0].time_range.start
