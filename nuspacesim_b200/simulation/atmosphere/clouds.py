@@ -22,7 +22,8 @@ import numpy as np
 
 from ... import _lib
 
-__all__ = ["CloudTopHeight", "us_std_atm_altitude_from_pressure", "pressure_map"]
+__all__ = ["CloudTopHeight", "us_std_atm_altitude_from_pressure",
+           "us_std_atm_pressure_from_altitude", "pressure_map"]
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "data",
                      "cloud_maps")
@@ -53,6 +54,24 @@ def us_std_atm_altitude_from_pressure(P):
         H = Hb + np.where(positive, np.where(isothermal, dh_iso, dh_grad), 0.0)
         z = _EARTH_RADIUS * H / (_EARTH_RADIUS - H)
     return np.where(positive, z, np.inf)
+
+
+def us_std_atm_pressure_from_altitude(z):
+    """Pressure [Pa] at geometric altitude z [km]: the inverse of the function above
+    (eas_optical/atmospheric_models.py:126-145)."""
+    z = np.asarray(z, dtype=np.float64)
+    finite = z < np.inf
+    with np.errstate(all="ignore"):
+        h = np.where(finite, z * _EARTH_RADIUS / (z + _EARTH_RADIUS), np.inf)
+    layer = np.zeros(h.shape, dtype=int)
+    for j in range(1, len(_H_B)):
+        layer[_H_B[j] <= h] = j
+    Hb, Lb, Tb, Pb = _H_B[layer], _LM_B[layer], _T_B[layer], _P_B[layer]
+    isothermal = Lb == 0
+    with np.errstate(all="ignore"):
+        f_iso = np.exp((-_GMR / Tb) * (h - Hb))
+        f_grad = (Tb / (Tb + Lb * (h - Hb))) ** (_GMR / Lb)
+    return np.where(finite, Pb * np.where(isothermal, f_iso, f_grad), Pb)
 
 
 def pressure_map(month: int, version=0) -> np.ndarray:

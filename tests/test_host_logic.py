@@ -351,6 +351,23 @@ def test_prep_column_totals_vs_brute_force():
         assert abs(f8[5] - Z) / Z < 2e-5, (b, a, f8[5], Z)
 
 
+def test_standard_atmosphere_round_trips():
+    """Mirrors the reference's test/simulation/eas_optical/test_atmospheric_models.py:30-46
+    for the two functions PressureMapCloud uses."""
+    from nuspacesim_b200.simulation.atmosphere import clouds as A
+
+    z = np.linspace(0.0, 100.0, 50000)
+    z1 = A.us_std_atm_altitude_from_pressure(A.us_std_atm_pressure_from_altitude(z))
+    assert np.allclose(z, z1) and np.all(np.isreal(z1))
+    p = np.linspace(1.01325e5, 1e-7, 50000)
+    p1 = A.us_std_atm_pressure_from_altitude(A.us_std_atm_altitude_from_pressure(p))
+    assert np.allclose(p, p1) and np.all(np.isreal(p1))
+    assert A.us_std_atm_altitude_from_pressure(0.0) == np.inf
+    # and against the oracle's restatement of the reference function
+    assert np.array_equal(A.us_std_atm_altitude_from_pressure(p),
+                          O.std_atm_altitude_from_pressure(p))
+
+
 def test_ozone_segment_shortcut_is_exact(emul):
     """ozone_segment_fast (one multiply, one floor, one comparison) against the ten-comparison
     definition for a dense float32 altitude grid and one ulp either side of every knot."""
