@@ -90,8 +90,10 @@ eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
 
 constexpr int WALK_BLOCK = 128;
 
+// The Gaisser-Hillas instantiation is capped at the Greisen one's 96 registers (20 warps/SM):
+// 8 bytes of spill, +1..2 % measured.
 template <bool GH>
-__global__ void __launch_bounds__(WALK_BLOCK)
+__global__ void __launch_bounds__(WALK_BLOCK, GH ? 5 : 1)
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
                 unsigned long long* __restrict__ stats) {
