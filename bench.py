@@ -160,8 +160,9 @@ def run_reference(args, rank):
     tot = sum(per_step)
     v = n * args.steps / tot
     line = dict(
-        metric=METRIC, value=v, unit=UNIT, n_gpus=0, steps=args.steps, warmup=args.warmup,
-        ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="weak",
+        # n_gpus echoes the launch (the driver pairs the two arms by it); no GPU is used
+        metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32 engine / f64 stages", data="synthetic", impl="reference",
         config=dict(workload=WORKLOAD, events_per_step=n,
                     note="the reference's own CPU algorithm for the path; /root/reference "
