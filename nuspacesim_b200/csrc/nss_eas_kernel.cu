@@ -90,10 +90,11 @@ eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
 
 constexpr int WALK_BLOCK = 128;
 
-// The Gaisser-Hillas instantiation is capped at the Greisen one's 96 registers (20 warps/SM):
-// 8 bytes of spill, +1..2 % measured.
+// 5 blocks of 4 warps per SM = 96 registers per thread, no spills in either instantiation:
+// 20 warps/SM is the measured optimum (24 warps at 80 registers spill and lose 3 %; left to
+// itself ptxas takes 112-114 registers = 16 warps/SM and loses 4 %).
 template <bool GH>
-__global__ void __launch_bounds__(WALK_BLOCK, GH ? 5 : 1)
+__global__ void __launch_bounds__(WALK_BLOCK, 5)
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
                 unsigned long long* __restrict__ stats) {
