@@ -580,7 +580,7 @@ def test_pressure_map_cloud_compute_and_acceptance(nss, tables_v3):
 # ------------------------------------------------------------------ sliced compute() pipeline
 
 
-@pytest.mark.parametrize("mode", ["philox", "uniforms", "gh_cloudmap_powerlaw"])
+@pytest.mark.parametrize("mode", ["philox", "uniforms", "uniforms_numpy", "gh_cloudmap_powerlaw"])
 def test_compute_sliced_pipeline_equals_unsliced(nss, mode, tmp_path):
     """compute() pipelined over slices of thrown events returns bit-identical columns (valid
     events keep their thrown order) and the same acceptance as the one-shot path; ragged last
@@ -596,6 +596,9 @@ def test_compute_sliced_pipeline_equals_unsliced(nss, mode, tmp_path):
         u4 = torch.from_numpy(rng.random((4, n))).pin_memory()
         kw["uniforms"] = dict(u4=u4, u_tau=torch.from_numpy(rng.random(n)).pin_memory(),
                               u_dec=rng.random(n))  # one NumPy array on purpose
+    if mode == "uniforms_numpy":
+        rng = np.random.default_rng(6)
+        kw["uniforms"] = dict(u4=rng.random((4, n)), u_tau=rng.random(n), u_dec=rng.random(n))
     if mode == "gh_cloudmap_powerlaw":
         cfg.simulation.eas_long_profile = "Gaisser-Hillas Fluctuated"
         cfg.simulation.cloud_model = PressureMapCloud(month=7)
