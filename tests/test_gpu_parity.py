@@ -363,6 +363,36 @@ def test_acceptance_properties_at_scale(nss):
     assert abs(m2 - mcint) < 5 * np.hypot(unc, u2)
 
 
+def test_acceptance_at_baseline_size(nss):
+    """BASELINE.json configs[2] size: 1e8 thrown events of the default physics through the fused
+    mode (1.7 s on a B200).  Size-independent properties: re-sharding the thrown-index range
+    over 8 "ranks" reproduces the counts exactly and the sums to 1e-12; the integral agrees with
+    the 1e6-event estimate of another seed within the combined Monte Carlo errors, and its own
+    error scales like 1/sqrt(N)."""
+    cfg = make_config()
+    n = 100_000_000
+    r = nss.AcceptanceRunner(cfg)
+    r.enqueue(1234, 0, n)
+    a = r.sums()
+    mcint, geo, npass, unc = r.finalize(a)
+    assert a[5] == n and 0.99 < a[4] / n < 0.995
+    r.reset()
+    from nuspacesim_b200.compute import shard_range
+
+    for rank in range(8):
+        lo, cnt = shard_range(n, rank, 8)
+        r.enqueue(1234, lo, cnt)
+    b = r.sums()
+    assert np.array_equal(a[3:6], b[3:6])
+    np.testing.assert_allclose(a[:3], b[:3], rtol=1e-12)
+    r.reset()
+    r.enqueue(99, 0, 1_000_000)
+    m2, _, _, u2 = r.finalize(r.sums())
+    assert abs(m2 - mcint) < 5 * np.hypot(unc, u2)
+    assert 0.08 < unc / u2 < 0.125  # sqrt(1e6 / 1e8) = 0.1
+    assert abs(geo - 3700.0) / 3700.0 < 0.01
+
+
 def test_mask_scan_and_compaction_ragged(nss):
     import ctypes as C
 
