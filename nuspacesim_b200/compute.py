@@ -42,7 +42,7 @@ COLUMN_GROUPS = (
 
 def compute(config, verbose: bool = False, output_file: str = None, to_plot: list = [],
             write_stages: bool = False, seed: int = 0, uniforms: dict = None,
-            slice_events: int = None):
+            slice_events: int = None, shard: bool = False):
     """Simulate an upward going shower (compute.py:73-298, optical branch).
 
     Extensions: ``seed`` keys the Philox streams (the reference uses the global unseeded
@@ -53,18 +53,36 @@ def compute(config, verbose: bool = False, output_file: str = None, to_plot: lis
     upload of the next slice's uniforms and the download of the previous slice's columns hide
     behind the EAS kernel.  Per-event results do not depend on the slicing; staged writes and
     plots use the unsliced path (they need whole columns after every stage).
+
+    ``shard=True`` with ``torch.distributed`` initialised (one process per GPU): rank r of G
+    simulates the contiguous block ``shard_range(N, r, G)`` of the thrown events and returns
+    ITS rows of the table (concatenating the ranks' tables in rank order gives the one-process
+    table; nothing per event is exchanged); the acceptance meta keys are global -- the ranks'
+    five sums are gathered once and merged exactly.
     """
     n_thrown = config.simulation.thrown_events
     if uniforms and "u4" in uniforms:
         n_thrown = int(uniforms["u4"].shape[1]) if getattr(uniforms["u4"], "ndim", 0) == 2 else 0
     step = SLICE_EVENTS if slice_events is None else int(slice_events)
-    sliced = (step > 0 and n_thrown >= 2 * step and not write_stages and not to_plot
-              and config.simulation.mode != "Target" and config.detector.optical.enable)
+    sliceable = (not write_stages and not to_plot and config.simulation.mode != "Target"
+                 and config.detector.optical.enable and n_thrown > 0)
+    sliced = step > 0 and n_thrown >= 2 * step and sliceable
+    lo, hi = 0, int(n_thrown)
+    if shard:
+        import torch.distributed as dist
+
+        if not sliceable:
+            raise ValueError("shard=True needs the optical branch without staged writes/plots")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            lo, cnt = shard_range(int(n_thrown), dist.get_rank(), dist.get_world_size())
+            hi = lo + cnt
+        sliced = True
+        step = step if step > 0 else SLICE_EVENTS
     try:
         with _lib.deferred_host_copies() as sink:
             if sliced:
                 return _compute_sliced(config, verbose, output_file, seed, uniforms, sink,
-                                       int(n_thrown), step)
+                                       int(n_thrown), step, lo, hi, shard)
             return _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms,
                             sink)
     finally:
@@ -190,7 +208,35 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
     return sim
 
 
-def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown, step):
+def _merge_sums(S):
+    """Rows of {sum f_geo, sum f, sum (f - mean)^2, n_pass, n_valid} -> one row (exact merge of
+    the squared deviations, Chan et al.)."""
+    S = np.asarray(S, dtype=np.float64).reshape(-1, 5)
+    S = S[S[:, 4] > 0]
+    if len(S) == 0:
+        return np.zeros(5)
+    n_valid = S[:, 4].sum()
+    mean = S[:, 1].sum() / n_valid
+    m2 = float((S[:, 2] + S[:, 4] * (S[:, 1] / S[:, 4] - mean) ** 2).sum())
+    return np.array([S[:, 0].sum(), S[:, 1].sum(), m2, S[:, 3].sum(), n_valid])
+
+
+def _gather_rank_sums(row):
+    """All ranks' merged sums (one 5-vector each) -> (world, 5) on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return row[None, :]
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(row, dtype=torch.float64, device=dev)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.stack([o.cpu().numpy() for o in out])
+
+
+def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown, step,
+                    first=0, last=None, shard=False):
     """compute() for large N: the same stage objects, called per slice of thrown events.
 
     Slice k owns thrown events [lo, hi); valid events keep their thrown order, so the result
@@ -211,9 +257,11 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     tau = Taus(config, seed=seed)
     eas = EAS(config, seed=seed)
     U = uniforms or {}
-    bounds = [(lo, min(lo + step, n_thrown)) for lo in range(0, n_thrown, step)]
+    last = n_thrown if last is None else last
+    bounds = [(lo, min(lo + step, last)) for lo in range(first, last, step)]
     logv(f"Running NuSpaceSim with Energy Spectrum ({config.simulation.spectrum})")
-    logv(f"Computing {n_thrown} thrown events in {len(bounds)} pipelined slices.")
+    logv(f"Computing thrown events [{first}, {last}) of {n_thrown} in {len(bounds)} pipelined "
+         "slices.")
 
     # uploads of every slice, in consumption order, on the side stream
     pre = []
@@ -227,7 +275,8 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
         pre.append(d)
 
     names = [n for g in COLUMN_GROUPS for n in g]
-    host = {n: torch.empty(n_thrown, dtype=torch.float64, pin_memory=True) for n in names}
+    host = {n: torch.empty(max(last - first, 1), dtype=torch.float64, pin_memory=True)
+            for n in names}
     WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2, "u_profile": 3}
     sums, off = [], 0
     thr = config.detector.optical.photo_electron_threshold
@@ -275,23 +324,23 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
                                     thr, mc_spec_norm, spec_weights_sum, device_sums=True))
         off += nv
 
-    logv(f"\tThrew {n_thrown} neutrinos. {off} were valid.")
-    if off == 0:
+    logv(f"\tThrew {last - first} neutrinos. {off} were valid.")
+    if off == 0 and not shard:
         print("\tWARNING: No valid events thrown! Exiting early! Check geometry!")
         return sim
-    S = torch.stack(sums).cpu().numpy()  # (slices, 8): sum geo, sum f, M2, n_pass, n_valid, ...
+    # (slices, 8) on the device: sum geo, sum f, M2, n_pass, n_valid, ... -> one host read
+    S = torch.stack(sums).cpu().numpy()[:, :5] if sums else np.zeros((0, 5))
     sink.synchronize()
     for group in COLUMN_GROUPS:
         sim.add_columns([host[n].numpy()[:off] for n in group], names=group)
+    mine = _merge_sums(S)
+    tot = _merge_sums(_gather_rank_sums(mine)) if shard else mine
     mcnorm = float(RegionGeom(config, seed=seed).mcnorm)
-    n_valid = S[:, 4].sum()
-    mean = S[:, 1].sum() / n_valid
     with np.errstate(invalid="ignore", divide="ignore"):
-        m2 = float((S[:, 2] + S[:, 4] * (S[:, 1] / S[:, 4] - mean) ** 2).sum())
-        mcunc = float(np.sqrt(m2 / (n_valid - 1.0) / n_thrown) * mcnorm)
-    mcint = float(S[:, 1].sum() * mcnorm / n_thrown)
-    mcintgeo = float(S[:, 0].sum() * mcnorm / n_thrown)
-    passEV = int(S[:, 3].sum())
+        mcunc = float(np.sqrt(tot[2] / (tot[4] - 1.0) / n_thrown) * mcnorm)
+    mcint = float(tot[1] * mcnorm / n_thrown)
+    mcintgeo = float(tot[0] * mcnorm / n_thrown)
+    passEV = int(tot[3])
     sim.meta["OMCINT"] = (mcint, "Optical MonteCarlo Integral")
     sim.meta["OMCINTGO"] = (mcintgeo, "Optical MonteCarlo Integral, GEO Only")
     sim.meta["ONEVPASS"] = (passEV, "Optical Number of Passing Events")

@@ -647,3 +647,64 @@ def test_compute_sliced_pipeline_equals_unsliced(nss, mode, tmp_path):
 
     back = R.read_fits_table(str(fn))
     assert np.array_equal(back["numPEs"], one["numPEs"])
+
+
+# ------------------------------------------------------------------ sharded column mode
+
+
+def _shard_worker(rank, world, port, n, seed, q):
+    import os
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)  # both ranks share the one GPU of the test box
+    import nuspacesim_b200 as nss
+    from conftest import make_config
+
+    sim = nss.compute(make_config(n=n), seed=seed, shard=True, slice_events=4096)
+    q.put((rank, {c: np.asarray(sim[c]).copy() for c in sim.colnames},
+           {k: sim.meta[k][0] for k in ("OMCINT", "OMCINTGO", "ONEVPASS", "OMCINTUN")}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_compute_sharded_over_ranks(nss):
+    """compute(shard=True) with two ranks (gloo; both on this box's GPU): each returns its own
+    block of rows, the blocks concatenate to the one-process table bit for bit, and every rank
+    holds the global acceptance."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    n, seed, world = 30_001, 23, 2
+    one = nss.compute(make_config(n=n), seed=seed, slice_events=0)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, n, seed, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(len(r[1]["numPEs"]) > 0.4 * len(one) for r in res)
+    for c in one.colnames:
+        assert np.array_equal(np.concatenate([r[1][c] for r in res]), one[c]), c
+    for r in res:
+        assert r[2]["ONEVPASS"] == one.meta["ONEVPASS"][0]
+        np.testing.assert_allclose(r[2]["OMCINT"], one.meta["OMCINT"][0], rtol=1e-13)
+        np.testing.assert_allclose(r[2]["OMCINTGO"], one.meta["OMCINTGO"][0], rtol=1e-13)
+        np.testing.assert_allclose(r[2]["OMCINTUN"], one.meta["OMCINTUN"][0], rtol=1e-10)
