@@ -75,3 +75,51 @@ def test_two_rank_sharded_acceptance_sums():
     fv = f[valid]
     np.testing.assert_allclose(f0[3], np.sqrt(np.var(fv, ddof=1) / n_total) * mcnorm, rtol=1e-9)
     assert f0[2] == np.count_nonzero(f)
+
+
+def _merge_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib
+
+    C = importlib.import_module("nuspacesim_b200.compute")
+    rng = np.random.default_rng(100 + rank)
+    # two "slices" per rank of per-event factors f (valid events only)
+    rows = []
+    for _ in range(2):
+        f = rng.random(1000 + 37 * rank) * (rng.random(1000 + 37 * rank) < 0.2)
+        rows.append([2 * f.sum(), f.sum(), ((f - f.mean()) ** 2).sum(), np.count_nonzero(f), f.size])
+    mine = C._merge_sums(np.array(rows))
+    tot = C._merge_sums(C._gather_rank_sums(mine))
+    q.put((rank, tot.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_column_mode_sum_merge():
+    """compute(shard=True)'s acceptance merge: per-slice sums -> per-rank -> global, with the
+    squared deviations combined exactly (the GPU test covers the columns)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_merge_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]
+    fs = []
+    for rank in range(world):
+        rng = np.random.default_rng(100 + rank)
+        for _ in range(2):
+            fs.append(rng.random(1000 + 37 * rank) * (rng.random(1000 + 37 * rank) < 0.2))
+    f = np.concatenate(fs)
+    tot = np.array(res[0][1])
+    np.testing.assert_allclose(tot[1], f.sum(), rtol=1e-13)
+    np.testing.assert_allclose(tot[2], ((f - f.mean()) ** 2).sum(), rtol=1e-11)
+    assert tot[3] == np.count_nonzero(f) and tot[4] == f.size
