@@ -88,13 +88,16 @@ eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
   }
 }
 
-constexpr int WALK_BLOCK = 128;
+// threads per block of the walk: one warp = one event in flight
+constexpr int walk_block(bool gh) { return gh ? 128 : 32; }
 
-// 5 blocks of 4 warps per SM = 96 registers per thread, no spills in either instantiation:
-// 20 warps/SM is the measured optimum (24 warps at 80 registers spill and lose 3 %; left to
-// itself ptxas takes 112-114 registers = 16 warps/SM and loses 4 %).
+// Occupancy (measured, tools/ab_bench.sh): left to itself ptxas takes 112-114 registers = 16
+// warps/SM (-4 %); 96 registers, no spills = 20 warps/SM; asking for >= 22 one-warp blocks
+// gives 80 registers = 25 warps/SM: 16 bytes of spill and 1 % faster for the Greisen
+// instantiation, 48 bytes of spill and 2-4 % slower for the Gaisser-Hillas one, which
+// therefore stays at 5 blocks of 4 warps and 96 registers.
 template <bool GH>
-__global__ void __launch_bounds__(WALK_BLOCK, 5)
+__global__ void __launch_bounds__(walk_block(GH), GH ? 5 : 22)
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
                 unsigned long long* __restrict__ stats) {
@@ -239,9 +242,9 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     err = gh ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<true>,
-                                                             WALK_BLOCK, 0)
+                                                             walk_block(true), 0)
              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<false>,
-                                                             WALK_BLOCK, 0);
+                                                             walk_block(false), 0);
     if (err != cudaSuccess) return (int)err;
     g_walk_blocks[gh] = sms * (per_sm > 0 ? per_sm : 1);
   }
@@ -264,7 +267,8 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
                                          g_conex_rows, u_profile, cloud_ev, P.cloud_top, n,
                                          g_scr.prep);
 
-  long long need = (n + (WALK_BLOCK / 32) - 1) / (WALK_BLOCK / 32);
+  const int wpb = walk_block(gh) / 32;  // warps (= events in flight) per block
+  long long need = (n + wpb - 1) / wpb;
   int blocks = (int)(need < g_walk_blocks[gh] ? need : g_walk_blocks[gh]);
   ProfRec* rec = nullptr;
   if (g_profile) {
@@ -278,11 +282,11 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     cudaEventRecord(rec->a, s);
   }
   if (gh)
-    eas_walk_kernel<true><<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc,
-                                                        g_scr.counter, stats);
+    eas_walk_kernel<true><<<blocks, walk_block(true), 0, s>>>(P, g_scr.prep, n, g_scr.acc,
+                                                              g_scr.counter, stats);
   else
-    eas_walk_kernel<false><<<blocks, WALK_BLOCK, 0, s>>>(P, g_scr.prep, n, g_scr.acc,
-                                                         g_scr.counter, stats);
+    eas_walk_kernel<false><<<blocks, walk_block(false), 0, s>>>(P, g_scr.prep, n, g_scr.acc,
+                                                                g_scr.counter, stats);
   if (rec) cudaEventRecord(rec->b, s);
   eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, g_scr.acc, g_scr.prep, n, o0, o1,
                                            dph, cang);
