@@ -492,13 +492,22 @@ def cloud_top_pressure_map(pressure_map, lat, long=None):
     return std_atm_altitude_from_pressure(m[i, j])
 
 
+ACCUM_MODES = {"exact": 0, "reference": 1}
+
+
 def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nthreads=1,
-             profile="Greisen", gh_rows=None):
+             profile="Greisen", gh_rows=None, accum="exact"):
     """CphotAng.__call__ (cphotang.py:703-724) -> (dphots, cang_deg, stats).
 
     ``profile`` is the reference's ``longitudinal_profile_func``; for "Gaisser-Hillas
     Fluctuated" ``gh_rows[i]`` is the CONEX row (columns 4..9) the reference would draw for
-    event i with ``np.random.randint`` (shower_properties.py:165-166)."""
+    event i with ``np.random.randint`` (shower_properties.py:165-166).
+
+    ``accum``: how the photon sum over (step, radial bin, energy decade) is accumulated --
+    "exact" (float64: the sum the reference's float32 terms actually have; what the CUDA
+    kernel is compared with) or "reference" (the ~1e5 sequential float32 additions
+    np.einsum(..., dtype=float32) performs at cphotang.py:521, replayed bit for bit; this is
+    3.0e-5 below "exact" on average and reproduces the reference to ~1e-6)."""
     beta = np.ascontiguousarray(beta, dtype=np.float64)
     alt = np.ascontiguousarray(alt, dtype=np.float64)
     es = np.ascontiguousarray(eshow100pev, dtype=np.float64)
@@ -508,10 +517,14 @@ def cphotang(beta, alt, eshow100pev, detector_altitude=525.0, cloud_top=None, nt
     t = _ctables()
     kind, rows_p, _keep = _profile_args(profile, gh_rows, n)
     hc, ctop, cev_p, _keep2 = _cloud_args(cloud_top, n)
-    _lib().nss_oracle_cphotang_profile(
-        ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es), hc, ctop,
-        ctypes.c_double(detector_altitude), _dp(d), _dp(c), ctypes.byref(st),
-        ctypes.c_int(nthreads), kind, rows_p, cev_p)
+    _lib().nss_oracle_set_accum_mode(ctypes.c_int(ACCUM_MODES[accum]))
+    try:
+        _lib().nss_oracle_cphotang_profile(
+            ctypes.byref(t), ctypes.c_int64(n), _dp(beta), _dp(alt), _dp(es), hc, ctop,
+            ctypes.c_double(detector_altitude), _dp(d), _dp(c), ctypes.byref(st),
+            ctypes.c_int(nthreads), kind, rows_p, cev_p)
+    finally:
+        _lib().nss_oracle_set_accum_mode(ctypes.c_int(0))
     return d, c, {k: getattr(st, k) for k, _ in _Stats._fields_}
 
 

@@ -135,9 +135,13 @@ def eas_large():
     for tag in EAS_LARGE_TAGS:
         b, a, e = (G[f"{tag}_{k}"] for k in ("beta_rad", "altDec", "showerEnergy"))
         d0, c0, _ = O.cphotang(b, a, e, 525.0, None, nthreads=os.cpu_count() or 1)
+        dr, _, _ = O.cphotang(b, a, e, 525.0, None, nthreads=os.cpu_count() or 1,
+                              accum="reference")
         sens = O.conditioning(b, a, e, 525.0, None, nthreads=os.cpu_count() or 1)
+        with np.errstate(all="ignore"):
+            deficit = np.where(d0 > 0, (d0 - dr) / d0, 0.0)
         out[tag] = dict(beta=b, alt=a, eshow=e, dphots=G[f"{tag}_dphots"], cang=G[f"{tag}_cang"],
-                        oracle_dphots=d0, oracle_cang=c0, sens=sens)
+                        oracle_dphots=d0, oracle_cang=c0, sens=sens, f32_sum_deficit=deficit)
     return out
 
 
@@ -223,6 +227,13 @@ def check_engine_vs_reference(d, c, ref, what, median_tol=5e-5, cang_tol=5e-5):
     assert np.percentile(r[live], 99) < 3e-4, (what, np.percentile(r[live], 99))
     if live.sum() >= 3000:  # below that the 99.9th percentile is just the largest event
         assert np.percentile(r[live], 99.9) < 2e-3, (what, np.percentile(r[live], 99.9))
+    if "f32_sum_deficit" in ref:
+        # The reference adds its ~1e5 photon-sum terms into a float32 one after the other
+        # (np.einsum, cphotang.py:521) and ends 3e-5 below their exact sum; with that deficit --
+        # computed by the oracle, independently of the implementation under test -- applied,
+        # an exact-sum implementation must land on the reference itself.
+        rc = rel_err(np.asarray(d) * (1.0 - ref["f32_sum_deficit"]), ref["dphots"])
+        assert np.median(rc[live]) < 5e-6, (what, np.median(rc[live]))
     bad = r > np.maximum(2.5e-3, 5 * ref["sens"])
     assert not bad.any(), (what, np.nonzero(bad)[0][:5], r[bad][:5])
     assert rel_err(c, ref["cang"]).max() < cang_tol, (what, rel_err(c, ref["cang"]).max())

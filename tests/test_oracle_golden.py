@@ -165,6 +165,54 @@ def test_engine_gaisser_hillas_reference_sample(eas_gh, tag, short):
                               median_tol=7e-5 if short == "ghf" else 5e-5)
 
 
+@pytest.mark.parametrize("tag", ("c1", "e10", "pl10"))
+def test_reference_float32_accumulation_is_the_residual(tag):
+    """Where the 3e-5 between the reference and any exact implementation comes from:
+    np.einsum("zje,zw->", ..., dtype=float32) (cphotang.py:521) adds its ~1e5 float32 terms one
+    after the other into a float32.  With that accumulation replayed (accum="reference") the
+    oracle reproduces the unmodified reference to a median of 4e-7 (libm-level); summed
+    exactly (accum="exact", what the CUDA kernel is checked against) the same terms give
+    3.0e-5 more.  Same for Gaisser-Hillas Fluctuated, whose longer profiles lose 5e-5."""
+    import os
+
+    from conftest import GOLDEN
+
+    nt = os.cpu_count() or 1
+    G = np.load(os.path.join(GOLDEN, "eas_large.npz"))
+    b, a, e = (G[f"{tag}_{k}"][:3000] for k in ("beta_rad", "altDec", "showerEnergy"))
+    ref = G[f"{tag}_dphots"][:3000]
+    d_ref, _, _ = O.cphotang(b, a, e, 525.0, None, nthreads=nt, accum="reference")
+    d_ex, _, _ = O.cphotang(b, a, e, 525.0, None, nthreads=nt, accum="exact")
+    r = rel_err(d_ref, ref)
+    assert np.median(r) < 1e-6 and np.percentile(r, 90) < 1e-5, (np.median(r), np.percentile(r, 90))
+    deficit = (d_ex - d_ref) / d_ex
+    assert 2.0e-5 < np.median(deficit) < 4.5e-5 and np.percentile(deficit, 2) > 0, np.median(deficit)
+    assert abs(np.median((d_ex - ref) / ref) - np.median(deficit)) < 3e-6
+    if tag == "c1":
+        H = np.load(os.path.join(GOLDEN, "eas_gh.npz"))
+        b, a, e = (H[f"c1_{k}"] for k in ("beta_rad", "altDec", "showerEnergy"))
+        rows = conex_rows()[H["c1_row"]]
+        d, _, _ = O.cphotang(b, a, e, 525.0, None, nthreads=nt, accum="reference",
+                             profile="Gaisser-Hillas Fluctuated", gh_rows=rows)
+        assert np.median(rel_err(d, H["c1_ghf_dphots"])) < 1e-6
+
+
+def test_einsum_float32_order_replayed_bit_for_bit():
+    """The accumulation order assumed by accum="reference", checked against NumPy itself:
+    for float32 operands einsum("zje,zw->") equals the sequential float32 running sum over
+    (z, j, e) in C order of svtrm[z,j,e] * sum_w sigval[z,w]."""
+    rng = np.random.default_rng(2)
+    sv = (rng.random((150, 40, 8)) ** 6 * 1e3).astype(np.float32)
+    sv[:, 25:, :] *= (rng.random((150, 15, 8)) < 0.5)  # masked-out bins are zeros
+    sg = (rng.random((150, 28)) ** 3).astype(np.float32)
+    want = np.einsum("zje,zw->", sv, sg, dtype=np.float32)
+    sgs = sg.sum(axis=1, dtype=np.float32)
+    got = np.cumsum((sv * sgs[:, None, None]).ravel(), dtype=np.float32)[-1]
+    exact = np.einsum("zje,zw->", sv.astype(np.float64), sg.astype(np.float64))
+    assert got == want
+    assert abs(float(want) - exact) / exact > 1e-6  # and it is measurably not the exact sum
+
+
 def test_conex_table_is_the_reference_table():
     """The shipped .npy holds columns 4..9 of the reference's CONEX file (cphotang.py:266-276)."""
     import os
