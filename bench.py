@@ -276,10 +276,10 @@ def main():
             unit="TFLOP/s", frac=ach / fp32_peak.value if fp32_peak.value else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE eas_walk_kernel launch of this
             # workload (2 Mi events) from the committed ncu --set full capture
-            # (profiles/r01_eas_v10_ncu_key_metrics.json): 306.3 MB + 87.3 MB.  The records the
+            # (profiles/r01_eas_v11_ncu_key_metrics.json): 306.6 MB + 86.2 MB.  The records the
             # kernel must move are 144 B (EasPrep) + 48 B (EasAcc) per event = 381 MB per
             # launch: no wasted re-reads; the kernel is compute bound (bound = "fp32").
-            traffic=393.64e6 if args.batch == 1 << 21 else None,
+            traffic=392.71e6 if args.batch == 1 << 21 else None,
             traffic_unit="bytes per launch (ncu, cold cache); algorithmic record bytes per "
                          "launch = 192 B x events",
             peak_source="nss_microbench_peaks on this device (FFMA chains; MEASURED_PEAKS.json "
