@@ -74,8 +74,9 @@ def time_cpu_path(n: int, cores: int, seed: int = 20240601):
     u4, ut, ud = rng.random((4, n)), rng.random(n), rng.random(n)
     O.build_c_oracle()
     t0 = time.perf_counter()
-    mc, _, _, _ = O.run_path(O.OracleParams(), tabs, u4, None, ut, ud, nthreads=cores)
+    mc, _, _, st = O.run_path(O.OracleParams(), tabs, u4, None, ut, ud, nthreads=cores)
     dt = time.perf_counter() - t0
+    time_cpu_path.last_eas_seconds = st.get("eas_seconds")
     return dt, mc
 
 
@@ -87,7 +88,10 @@ def cpu_baseline(target_s: float, cores: int):
     return dict(value=n / dt, unit=UNIT, cores=cores, kind="port",
                 sample=f"{n} thrown events of the same workload in {dt:.1f} s "
                        f"(oracle/: C engine with OpenMP over events + NumPy stages)",
-                mcint=mc[0], mcint_unc=mc[3])
+                mcint=mc[0], mcint_unc=mc[3],
+                eas_stage_share=(time_cpu_path.last_eas_seconds or 0.0) / dt,
+                eas_stage_value=n / time_cpu_path.last_eas_seconds
+                if time_cpu_path.last_eas_seconds else None)
 
 
 class ClockSampler:

@@ -613,8 +613,13 @@ def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1, u_pr
         # compute.py:214-216: cloudf(init_lat, init_long) at the ground spot of each trajectory
         lat0, _ = geom_lat_long(g, t, np.zeros(int(m.sum())))
         cloud_ev = cloud_top_pressure_map(p.cloud_map, lat0)
+    import time
+
+    t_eas = time.perf_counter()
     npe, cth, d, c, st = eas(p, beta, alt, sh, nthreads=nthreads, gh_rows=rows,
                              cloud_ev=cloud_ev)
+    st["eas_seconds"] = time.perf_counter() - t_eas  # the EAS stage alone (bench cpu_baseline)
+    st["n_valid"] = int(m.sum())
     mc = mcintegral(g, t, npe, cth, pex, p.photo_electron_threshold, sn, sw)
     cols = dict(beta_rad=beta, theta_rad=t["thetaTrSubV"][m], path_len=t["losPathLen"][m],
                 log_e_nu=le, tauBeta=tb, tauLorentz=lor, tauEnergy=te, showerEnergy=sh,
