@@ -92,10 +92,8 @@ int nss_geom_throw_u(const NssParams* p, const double* u4xn, int64_t n, const Ns
 int nss_geom_throw_philox(const NssParams* p, uint64_t seed, uint64_t first_event, int64_t n,
                           const NssGeomSoA* out, void* stream);
 
-/* Exclusive scan of a byte mask -> int64 positions, and the number of set entries (int64 at
- * n_set: device memory, or pinned host memory under unified addressing -- the kernel then
- * writes the count straight to the host and no device-to-host copy is needed).
- * workspace: nss_scan_workspace_bytes(n) bytes. */
+/* Exclusive scan of a byte mask -> int64 positions, and the number of set entries
+ * (device int64 at n_set).  workspace: nss_scan_workspace_bytes(n) bytes. */
 int64_t nss_scan_workspace_bytes(int64_t n);
 int nss_mask_scan(const uint8_t* mask, int64_t n, int64_t* pos, int64_t* n_set, void* workspace,
                   void* stream);

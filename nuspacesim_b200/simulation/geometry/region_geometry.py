@@ -95,22 +95,14 @@ class RegionGeom:
         L = _lib.lib()
         n = self._n
         self._pos = _lib.empty(max(n, 1), "int64")
-        # The count is written by the scan kernel straight into pinned host memory (unified
-        # addressing: the host pointer is valid on the device) and read after an event, so the
-        # one host synchronisation of a throw does not queue a device-to-host copy behind the
-        # column copies that keep the copy engine busy in compute().
-        torch = _lib.torch_cuda()
-        nset = torch.zeros(1, dtype=torch.int64).pin_memory()
+        nset = _lib.zeros(1, "int64")
         ws = _lib.empty(max(int(L.nss_scan_workspace_bytes(n)), 8), "uint8")
         _lib.check(
             L.nss_mask_scan(_lib.ptr(self._dev["event_mask"]), n, _lib.ptr(self._pos),
-                            C.c_void_p(nset.data_ptr()), _lib.ptr(ws), _lib.stream_ptr()),
+                            _lib.ptr(nset), _lib.ptr(ws), _lib.stream_ptr()),
             "nss_mask_scan",
         )
-        done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream())
-        done.synchronize()
-        self._n_valid = int(nset[0])
+        self._n_valid = int(nset.item())
 
     def compact(self, full, device: bool = True):
         """Entries of a length-N (thrown-order) array that belong to valid events, in thrown
