@@ -2,6 +2,8 @@
 // lane group of width 1 so the kernel's arithmetic can be compared with the oracle in a
 // container that has no GPU.  Never loaded by the product package.
 //   g++ -O2 -ffp-contract=off -shared -fPIC -I nuspacesim_b200/csrc tests/host_emul/eas_host_emul.cpp
+#include <stdlib.h>
+
 #include "nss_eas_core.cuh"
 #include "nss_eas_tables.h"
 
@@ -11,6 +13,7 @@ struct Ops1 {
   static int lane() { return 0; }
   static float scan_f(float v) { return v; }
   static double sum_d(double v) { return v; }
+  static float sum_f(float v) { return v; }
   static int sum_i(int v) { return v; }
   static int max_i(int v) { return v; }
   static int min_i(int v) { return v; }
@@ -42,6 +45,12 @@ extern "C" int nss_emul_eas_profile(long long n, const double* beta, const doubl
   P.profile = profile;
   P.pad = 0;
   nss::EasStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  // events are independent; tools/emul_eval.py builds this with -fopenmp (the counters are
+  // then merged per thread), the test build is serial
+#pragma omp parallel
+  {
+  nss::EasStats stl = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma omp for schedule(dynamic, 64)
   for (long long i = 0; i < n; ++i) {
     double d = 0.0, c = 1.5;
     if (!(alt[i] < 0.0 || alt[i] > 20.0)) {
@@ -51,9 +60,9 @@ extern "C" int nss_emul_eas_profile(long long n, const double* beta, const doubl
       nss::eas_prep(T, beta[i], alt[i], eshow[i], true, profile,
                     profile == 2 ? gh_rows + 6 * i : nullptr, ct, E);
       if (profile == 0)
-        nss::eas_walk<Ops1, false>(T, P, E, 0.0f, E.cloud, A, &st, true);
+        nss::eas_walk<Ops1, false>(T, P, E, 0.0f, E.cloud, A, &stl, true);
       else
-        nss::eas_walk<Ops1, true>(T, P, E, 0.0f, E.cloud, A, &st, true);
+        nss::eas_walk<Ops1, true>(T, P, E, 0.0f, E.cloud, A, &stl, true);
       nss::eas_finish(P, beta[i], alt[i], A, E.cloud, d, c);
     }
     double npe, cc;
@@ -63,9 +72,17 @@ extern "C" int nss_emul_eas_profile(long long n, const double* beta, const doubl
     if (dphots) dphots[i] = d;
     if (cang) cang[i] = c;
   }
+#pragma omp critical
+  {
+    st.n_events += stl.n_events; st.n_raw += stl.n_raw; st.n_val += stl.n_val;
+    st.J += stl.J; st.JNe += stl.JNe; st.n_exp += stl.n_exp;
+    st.reserved += stl.reserved;
+  }
+  }
   if (stats6) {
     stats6[0] = st.n_events; stats6[1] = st.n_raw; stats6[2] = st.n_val;
     stats6[3] = st.J; stats6[4] = st.JNe; stats6[5] = st.n_exp;
+    if (getenv("NSS_EMUL_LIGHT")) stats6[5] = st.reserved;  // steps only counted (tail)
   }
   return 0;
 }
