@@ -20,10 +20,14 @@ one all-reduce of 8 float64 acceptance sums per step.
          algorithmic FLOPs (8(d) formula evaluated on the kernel's own work counters) /
          CUDA-event duration of the launches inside the timed region; peak = FP32 FMA rate
          measured on this device by nss_microbench_peaks ("of measured").
-  cpu_baseline  the oracle port (oracle/: C engine + NumPy stages) on the box's host cores,
-         bounded sample of the same workload.
+  cpu_baseline  the UNMODIFIED reference (kind "reference": its own source files, staged into
+         oracle/_ref/ by build() and run through oracle/ref_bench.py with the EAS stage fanned
+         out over all host cores like its dask bag) on a bounded sample of the same workload;
+         the oracle's C/OpenMP port beside it (cpu_baseline.port), and one core alone.
+  workloads  events/s (device-resident, 1e7 events, this GPU) of BASELINE.json configs 3/4 and
+         the non-default shower profiles / cloud model, each with its own work per event.
 
---impl reference times that CPU implementation alone (rank 0 only).
+--impl reference times the reference's CPU implementation alone (rank 0 only).
 """
 from __future__ import annotations
 
@@ -94,6 +98,42 @@ def cpu_baseline(target_s: float, cores: int):
                 if time_cpu_path.last_eas_seconds else None)
 
 
+def time_reference(n: int, procs: int, seed: int = 1):
+    """The unmodified reference on n thrown events (oracle/ref_bench.py in its own process:
+    it forks workers and installs stub modules).  -> dict or None if it cannot run here."""
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_bench", "--events", str(int(n)),
+                            "--procs", str(int(procs)), "--seed", str(int(seed))],
+                           cwd=ROOT, capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return None
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def reference_baseline(target_s: float, cores: int):
+    """Calibrate on 2000 events, then time a sample sized for ~target_s seconds; plus one core
+    on 1e3 events (SURVEY.md 8(d) CPU baseline plan)."""
+    cal = time_reference(2000, cores)
+    if cal is None:
+        return None
+    n = int(max(2000, min(2_000_000, 2000 * target_s / max(cal["seconds"], 1e-3))))
+    r = time_reference(n, cores, seed=2)
+    if r is None:
+        return None
+    one = time_reference(1000, 1, seed=3)
+    return dict(value=r["events_per_s"], unit=UNIT, cores=cores, kind="reference",
+                sample=f"{n} thrown events of the same workload in {r['seconds']:.1f} s: the "
+                       f"reference's own source files ({r['source']} copy) -- NumPy stages "
+                       f"single-threaded, CphotAng.run over {cores} worker processes "
+                       "(multiprocessing in place of its dask bag, cphotang.py:719-723)",
+                mcint=r["mcint"], mcint_unc=r["mcint_unc"], eas_stage_share=r["eas_seconds"] / r["seconds"],
+                eas_stage_value=r["eas_events_per_s"],
+                single_core=None if one is None else dict(
+                    value=one["events_per_s"], events=one["events"], seconds=one["seconds"]))
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -155,29 +195,132 @@ def run_reference(args, rank):
         return
     cores = os.cpu_count() or 1
     per_step = []
-    dt, _ = time_cpu_path(2000, cores)
-    n = int(max(2000, min(500_000, 2000 * 8.0 / max(dt, 1e-3))))  # ~8 s per step
-    for i in range(args.warmup + args.steps):
-        dt, mc = time_cpu_path(n, cores, seed=100 + i)
-        if i >= args.warmup:
-            per_step.append(dt)
+    cal = time_reference(2000, cores)
+    kind = "reference" if cal is not None else "port"
+    if cal is not None:
+        n = int(max(2000, min(500_000, 2000 * 8.0 / max(cal["seconds"], 1e-3))))  # ~8 s per step
+        src = cal["source"]
+        for i in range(args.warmup + args.steps):
+            r = time_reference(n, cores, seed=100 + i)
+            if r is None:
+                kind = "port"
+                break
+            if i >= args.warmup:
+                per_step.append(r["seconds"])
+    if kind == "port":  # no staged reference on this machine: the oracle's restatement
+        per_step = []
+        dt, _ = time_cpu_path(2000, cores)
+        n = int(max(2000, min(500_000, 2000 * 8.0 / max(dt, 1e-3))))
+        for i in range(args.warmup + args.steps):
+            dt, mc = time_cpu_path(n, cores, seed=100 + i)
+            if i >= args.warmup:
+                per_step.append(dt)
     tot = sum(per_step)
     v = n * args.steps / tot
+    what = (f"the UNMODIFIED reference ({src} copy of its source files, oracle/ref_bench.py): "
+            "NumPy stages single-threaded, CphotAng.run over all host cores"
+            if kind == "reference" else
+            "the oracle port (C engine + NumPy stages): no staged reference on this machine")
     line = dict(
         # n_gpus echoes the launch (the driver pairs the two arms by it); no GPU is used
         metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
         warmup=args.warmup, ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32 engine / f64 stages", data="synthetic", impl="reference",
-        config=dict(workload=WORKLOAD, events_per_step=n,
-                    note="the reference's own CPU algorithm for the path; /root/reference "
-                         "cannot travel to the GPU box (astropy/h5py/dask absent), so this is "
-                         "the oracle port pinned to it by tests/golden"),
-        cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
+        config=dict(workload=WORKLOAD, events_per_step=n, implementation=what,
+                    note="same physics and metric as the B200 arm; each step is a BOUNDED "
+                         f"sample of {n} thrown events of that workload (the full 1e7 would "
+                         "take hours on the host), so the rate, not the step size, is compared"),
+        cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind=kind,
                           sample=f"{n} thrown events per step"),
         e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ secondary workloads
+
+
+def workload_configs(nss):
+    """BASELINE.json configs[2] (energy sweep) and [3] (power law, wide angle), the two
+    Gaisser-Hillas profiles and the pressure-map cloud model -> {name: (config, description)}."""
+    import math
+
+    from nuspacesim_b200.config import PowerSpectrum, PressureMapCloud
+
+    out = {}
+    for tag, le in (("e7", 7.0), ("e9", 9.0), ("e10", 10.0)):
+        c = nss.NssConfig()
+        c.simulation.spectrum.log_nu_energy = le
+        out[tag] = (c, f"monospectrum log_nu_energy={le}")
+    c = nss.NssConfig()
+    c.simulation.spectrum = PowerSpectrum(index=2.0, lower_bound=6.0, upper_bound=12.0)
+    c.simulation.max_cherenkov_angle = math.radians(10.0)
+    out["powerlaw_w10"] = (c, "power-law spectrum (index 2, 1e6-1e12 GeV), max_cherenkov_angle 10 deg")
+    for tag, prof in (("ghp", "Gaisser-Hillas Parameterized"), ("ghf", "Gaisser-Hillas Fluctuated")):
+        c = nss.NssConfig()
+        c.simulation.eas_long_profile = prof
+        out[tag] = (c, f"monospectrum 8.0, {prof} longitudinal profile")
+    c = nss.NssConfig()
+    c.simulation.cloud_model = PressureMapCloud(month=7)
+    out["cloudmap"] = (c, "monospectrum 8.0, PressureMapCloud month 7 (per-event cloud tops)")
+    return out
+
+
+def bench_workloads(nss, torch, n, batch, first):
+    res = {}
+    for name, (cfg, desc) in workload_configs(nss).items():
+        r = nss.AcceptanceRunner(cfg, batch=batch, collect_stats=True)
+        r.enqueue(SEED, first, min(n, batch))  # warm-up (tables, CONEX / cloud map upload)
+        torch.cuda.synchronize()
+        r.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.enqueue(SEED, first, n)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        st = r.stats.cpu().numpy().astype(float)
+        mc = r.finalize(r.sums(False))
+        ne = max(st[0], 1.0)
+        flops, transc = algorithmic_work(st)
+        res[name] = dict(
+            value=n / ms * 1e3, unit=UNIT, ms=ms, events=n, config=desc,
+            acceptance=dict(mcint=mc[0], geo=mc[1], n_pass=mc[2], unc=mc[3]),
+            eas_events_fraction=st[0] / n,
+            work_per_eas_event=dict(N_raw=st[1] / ne, N_val=st[2] / ne, J=st[3] / ne,
+                                    JNe=st[4] / ne, exp_evaluated=st[5] / ne),
+            algorithmic_tflops=flops / (ms * 1e-3) * 1e-12)
+        del r
+    return res
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one eas_walk_kernel launch from the
+    newest committed `ncu --set full` summary (profiles/r*_eas_v*_ncu_key_metrics.json)."""
+    import glob
+    import re
+
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", "r*_eas_v*_ncu_key_metrics.json")):
+        m = re.search(r"r(\d+)_eas_v(\d+)_", os.path.basename(f))
+        if m and (best is None or (int(m.group(1)), int(m.group(2))) > best[0]):
+            best = ((int(m.group(1)), int(m.group(2))), f)
+    if best is None:
+        return None, None, None
+    try:
+        with open(best[1]) as fh:
+            d = json.load(fh)
+        def nbytes(v):
+            if isinstance(v, dict):  # {"value": "306.5", "unit": "Mbyte"}
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[v["unit"]]
+                return float(v["value"]) * scale
+            return float(v)
+
+        rd, wr = nbytes(d["dram__bytes_read.sum"]), nbytes(d["dram__bytes_write.sum"])
+        return rd + wr, d.get("events_in_launch"), os.path.relpath(best[1], ROOT)
+    except Exception:
+        return None, None, os.path.relpath(best[1], ROOT)
 
 
 # ------------------------------------------------------------------ the B200 arm
@@ -194,6 +337,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -275,17 +419,21 @@ def main():
         _lib.check(L.nss_microbench_peaks(C.byref(fp32_peak), C.byref(mufu_peak),
                                           _lib.stream_ptr()))
         ach = flops_step / eas_s_per_step * 1e-12
+        traffic, traffic_events, traffic_src = ncu_traffic()
+        ev_per_launch = float(st[0]) / launches_per_step
+        if traffic is not None and traffic_events:
+            # the capture's launch may hold a different number of events than this run's
+            traffic = traffic * ev_per_launch / float(traffic_events)
         line_extra["roofline"] = dict(
             bound="fp32", kernel="eas_walk_kernel", achieved=ach, peak=fp32_peak.value,
             unit="TFLOP/s", frac=ach / fp32_peak.value if fp32_peak.value else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE eas_walk_kernel launch of this
-            # workload (2 Mi events) from the committed ncu --set full capture
-            # (profiles/r01_eas_v11_ncu_key_metrics.json): 306.6 MB + 86.2 MB.  The records the
-            # kernel must move are 144 B (EasPrep) + 48 B (EasAcc) per event = 381 MB per
-            # launch: no wasted re-reads; the kernel is compute bound (bound = "fp32").
-            traffic=392.71e6 if args.batch == 1 << 21 else None,
-            traffic_unit="bytes per launch (ncu, cold cache); algorithmic record bytes per "
-                         "launch = 192 B x events",
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE eas_walk_kernel launch, read from
+            # the newest committed ncu --set full summary under profiles/ (scaled to this run's
+            # events per launch).  The records the kernel must move are 144 B (EasPrep) + 48 B
+            # (EasAcc) per event: the kernel is compute bound (bound = "fp32").
+            traffic=traffic, traffic_source=traffic_src,
+            traffic_unit="bytes per launch (ncu, cold cache)",
+            algorithmic_bytes=192.0 * ev_per_launch,
             peak_source="nss_microbench_peaks on this device (FFMA chains; MEASURED_PEAKS.json "
                         "has no FP32 entry), of measured",
             sfu=dict(achieved=transc_step / eas_s_per_step * 1e-12, peak=mufu_peak.value,
@@ -346,7 +494,11 @@ def main():
                    api="nuspacesim_b200.compute(config, uniforms=<pinned host arrays>) -> "
                        "15-column table + OMCINT meta on the host",
                    mcint=float(sim.meta["OMCINT"][0]), n_valid=len(sim),
-                   per_rank_s=per_rank, rank0_call_s=step_s)
+                   per_rank_s=per_rank, rank0_call_s=step_s,
+                   # first compute() call of this process (library and CUDA context already
+                   # up from the device-resident leg; no page-locked host memory cached yet):
+                   # what a one-shot `nuspacesim run` pays on top of start-up
+                   cold_call_s=step_s[0], cold_value=n / step_s[0])
 
     if rank == 0:
         line = dict(
@@ -357,13 +509,27 @@ def main():
                         seed=SEED, rng="in-kernel Philox4x32-10, counter = thrown-event index",
                         parallelism=f"event-sharded x{world}, one 8-double all-reduce per step",
                         l2="no input arrays; per-batch stage buffers (%.0f MB) exceed the 126 MB L2"
-                           % (args.batch * 65 / 1e6)),
+                           % (args.batch * 65 / 1e6),
+                        cpu_arm="cpu_baseline and `--impl reference` time the same workload's "
+                                "RATE on a bounded sample of it (1e4-1e5 thrown events per "
+                                "step: 1e7 would take hours on the host)"),
             acceptance=dict(mcint=mc[0], geo=mc[1], n_pass=mc[2], unc=mc[3]),
             clocks=clk, gpu_launches=int(gpu_launches), e2e=e2e,
         )
         line.update(line_extra)
+        if not args.no_workloads:
+            line["workloads"] = bench_workloads(nss, torch, n, args.batch,
+                                                first_event(args.warmup + args.steps))
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
+            cores = os.cpu_count() or 1
+            port = cpu_baseline(min(args.cpu_seconds, 8.0), cores)
+            ref = reference_baseline(args.cpu_seconds, cores)
+            if ref is not None:
+                ref["port"] = port
+                line["cpu_baseline"] = ref
+            else:
+                port["note"] = "no staged reference on this machine (oracle/_ref/): port only"
+                line["cpu_baseline"] = port
         print(json.dumps(line, default=float))
     if world > 1:
         dist.barrier()

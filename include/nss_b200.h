@@ -3,7 +3,12 @@
  *
  * Conventions
  *   - every array pointer is a RAW DEVICE POINTER owned by the caller (float64 unless
- *     noted, C-contiguous); nothing is allocated or freed inside except NssTables;
+ *     noted, C-contiguous).  The compute entry points allocate, free and synchronise nothing:
+ *     scratch is a caller-supplied `workspace` (nss_*_workspace_bytes), so calls on different
+ *     streams or host threads with distinct workspaces run concurrently.  Device memory is
+ *     owned by the library only behind the three REGISTRATION calls -- nss_tables_create /
+ *     nss_tables_free, nss_eas_set_conex_table, nss_cloud_set_altitude_map -- which
+ *     synchronise and must not run concurrently with launches that use what they replace;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the
  *     functions return without synchronising (except nss_tables_create);
  *   - return value: 0 = ok, < 0 = bad argument (NSS_E_*), > 0 = cudaError_t;
@@ -101,6 +106,13 @@ int nss_mask_scan(const uint8_t* mask, int64_t n, int64_t* pos, int64_t* n_set, 
  * region_geometry.py:241-287).  `to_radians` != 0 multiplies by pi/180 (beta_rad()). */
 int nss_compact_f64(const uint8_t* mask, const int64_t* pos, const double* in, double* out,
                     int64_t n, int to_radians, void* stream);
+/* The same for `ncols` <= NSS_COMPACT_MAX_COLS columns in one launch (mask and pos are read
+ * once per event, not once per column).  `in`, `out` and `to_radians` (optional) are HOST
+ * arrays of length ncols holding device pointers resp. flags. */
+#define NSS_COMPACT_MAX_COLS 16
+int nss_compact_columns_f64(const uint8_t* mask, const int64_t* pos, const double* const* in,
+                            double* const* out, const int* to_radians, int ncols, int64_t n,
+                            void* stream);
 
 /* Uniform `which` (0 = spectrum, 1 = tau energy, 2 = decay length, 3 = spare) of the per-event
  * Philox stream 1 -- the words the fused nss_run_acceptance consumes -- for thrown events
@@ -124,13 +136,19 @@ int nss_spectrum_powerlaw(const NssParams* p, const double* u, int64_t n, double
 /* Taus.tau_exit_prob (taus.py:99-122). flags: device int32 (NSS_FLAG_*), may be NULL. */
 int nss_tau_exit_prob(const NssTables* t, const double* betas, const double* log_e_nu, int64_t n,
                       double* pexit, int32_t* flags, void* stream);
-/* Taus.tau_energy (taus.py:124-146): inverse-CDF sample with one uniform per event. */
+/* Taus.tau_energy (taus.py:124-146): inverse-CDF sample with one uniform per event.
+ * u_raw == 0: u is used as it is, like the reference's `u` argument (outside (cdf[0], cdf[-1]]
+ * of the event's blended CDF row -> NSS_FLAG_U_RANGE).  u_raw != 0: u is a plain (0, 1) draw
+ * and is mapped onto (cdf[0], 1) of that row first, u' = c0 + (1 - c0) u -- the reference's own
+ * draw np.random.uniform(cdfs[:, 0], 1.0) (S/utils/cdf.py:419-423); identical for tables whose
+ * first CDF column is 0 (nupyprop), required for nuleptonsim (c0 up to 0.0134). */
 int nss_tau_energy(const NssTables* t, const double* betas, const double* log_e_nu,
-                   const double* u, int64_t n, double* tau_energy, int32_t* flags, void* stream);
+                   const double* u, int u_raw, int64_t n, double* tau_energy, int32_t* flags,
+                   void* stream);
 /* Taus.__call__ (taus.py:154-183): all five columns in one launch. */
 int nss_tau_sample(const NssParams* p, const NssTables* t, const double* betas,
-                   const double* log_e_nu, const double* u, int64_t n, double* tauBeta,
-                   double* tauLorentz, double* tauEnergy, double* showerEnergy,
+                   const double* log_e_nu, const double* u, int u_raw, int64_t n,
+                   double* tauBeta, double* tauLorentz, double* tauEnergy, double* showerEnergy,
                    double* tauExitProb, int32_t* flags, void* stream);
 
 /* EAS.altDec (S/simulation/eas_optical/eas.py:61-81). */
@@ -145,19 +163,22 @@ int nss_alt_dec(const double* beta, const double* tauBeta, const double* tauLore
  * (S/simulation/eas_optical/shower_properties.py:165).  dphots/cang (optional) are
  * CphotAng's own outputs [photons/m^2, degrees].  stats (optional): 8 device uint64 work
  * counters {events, raw z-steps N_raw, retained steps N_val, radial bins J, J*N_e, exp
- * evaluations in the radial x energy loop, N_val*N_e, reserved} -- the terms of SURVEY.md
- * 8(d)'s algorithmic-work formula, accumulated over the events that ran.  The library keeps a
- * per-process scratch (144 + 48 bytes per event of the largest call so far). */
+ * evaluations in the radial x energy loop, N_val*N_e, tail steps only counted} -- the terms
+ * of SURVEY.md 8(d)'s algorithmic-work formula, accumulated over the events that ran.
+ * workspace: nss_eas_workspace_bytes(n) bytes of device memory (the per-event records the
+ * three kernels hand to each other, 144 + 48 bytes per event, and the work counter of the
+ * persistent walk kernel); it may be reused by the next call on the SAME stream. */
+int64_t nss_eas_workspace_bytes(int64_t n);
 int nss_eas_optical(const NssParams* p, const double* beta, const double* altDec,
                     const double* showerEnergy, const uint8_t* mask, const double* u_profile,
                     const double* cloud_top_ev, int64_t n, double* numPEs,
                     double* costhetaChEff, double* dphots, double* cang,
-                    unsigned long long* stats, void* stream);
+                    unsigned long long* stats, void* workspace, void* stream);
 /* CphotAng.__call__ alone (no altDec mask, no EAS tail). */
 int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
                  const double* Eshow100PeV, const double* u_profile,
                  const double* cloud_top_ev, int64_t n, double* dphots, double* cang,
-                 unsigned long long* stats, void* stream);
+                 unsigned long long* stats, void* workspace, void* stream);
 /* `cloud_top_ev` (required when p->has_cloud == 2, else ignored): the value cloudf(lat, long)
  * returns for each event [km] (cphotang.py:644).
  *
@@ -179,7 +200,8 @@ int nss_eas_set_conex_table(const double* rows_host, int nrows);
 /* Per-launch timing of the EAS kernel with CUDA events recorded on the launching stream
  * (for bench.py's roofline: the kernel runs inside nss_run_acceptance).  enable(1) starts
  * recording; collect() synchronises the recorded events, returns the summed duration and
- * the number of launches, and clears the list. */
+ * the number of launches, and clears the list.  A measurement aid with process-global state:
+ * enable it only around single-threaded, single-stream use. */
 int nss_eas_profile_enable(int on);
 int nss_eas_profile_collect(double* total_ms, int64_t* launches);
 

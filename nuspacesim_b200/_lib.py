@@ -85,6 +85,9 @@ SIGNATURES = {
                                 C.c_void_p]),
     "nss_compact_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_int, C.c_void_p]),
+    "nss_compact_columns_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int,
+                                          C.c_int64, C.c_void_p]),
     "nss_event_uniforms": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p]),
     "nss_geom_lat_long": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 7 + [C.c_int64] +
@@ -93,15 +96,16 @@ SIGNATURES = {
                                         C.c_void_p]),
     "nss_tau_exit_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
-    "nss_tau_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nss_tau_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nss_tau_sample": (C.c_int, [C.POINTER(NssParams), C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
+                                 C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 7),
     "nss_alt_dec": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 3),
+    "nss_eas_workspace_bytes": (C.c_int64, [C.c_int64]),
     "nss_eas_optical": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 6 + [C.c_int64] +
-                        [C.c_void_p] * 6),
+                        [C.c_void_p] * 7),
     "nss_cphotang": (C.c_int, [C.POINTER(NssParams)] + [C.c_void_p] * 5 + [C.c_int64] +
-                     [C.c_void_p] * 4),
+                     [C.c_void_p] * 5),
     "nss_cloud_set_altitude_map": (C.c_int, [c_f64p, C.c_int, C.c_int, c_f64p, c_f64p]),
     "nss_cloud_top_from_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p]),
@@ -250,6 +254,14 @@ def empty(n, dtype="float64"):
 def zeros(n, dtype="float64"):
     torch = torch_cuda()
     return torch.zeros(int(n), dtype=getattr(torch, dtype), device="cuda")
+
+
+def eas_workspace(n):
+    """Device scratch for one nss_eas_optical / nss_cphotang call of n events (torch's caching
+    allocator hands the same block back to the next call on the same stream)."""
+    torch = torch_cuda()
+    return torch.empty(int(lib().nss_eas_workspace_bytes(int(n))), dtype=torch.uint8,
+                       device="cuda")
 
 
 def ptr(t) -> C.c_void_p:

@@ -15,6 +15,7 @@ are all-reduced (the only exchange step on the path).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Iterable
 
 import numpy as np
@@ -32,6 +33,11 @@ __all__ = ["compute", "run_acceptance"]
 
 #: thrown events per slice of compute()'s pipelined path (the acceptance mode's batch size)
 SLICE_EVENTS = 1 << 21
+#: slices whose uniforms are uploaded ahead of the one being computed
+PREFETCH_SLICES = 2
+#: result columns larger than this in total are not page-locked (pinning is ~1 GB/s and
+#: page-locked memory is a scarce resource: 120 B per thrown event)
+PINNED_MAX_BYTES = int(os.environ.get("NSS_PINNED_MAX_BYTES", 16 << 30))
 
 COLUMN_GROUPS = (
     ("beta_rad", "theta_rad", "path_len"), ("init_lat", "init_lon"), ("log_e_nu",),
@@ -177,8 +183,11 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
         n_valid, store=sw, plot=to_plot, device=True, u=valid_u("u_spec"))
 
     logv("Computing Taus.")
+    # the caller's u_tau is used as it is (shared-input parity with the reference's `u`
+    # argument); Philox and host-drawn uniforms are plain draws the kernel maps onto
+    # (cdf[0], 1) like the reference's own np.random.uniform(cdfs[:, 0], 1.0)
     tauBeta, tauLorentz, tauEnergy, showerEnergy, tauExitProb = tau(
-        beta_tr, log_e_nu, store=sw, plot=to_plot, u=valid_u("u_tau"))
+        beta_tr, log_e_nu, store=sw, plot=to_plot, u=valid_u("u_tau"), u_raw="u_tau" not in Ud)
 
     logv("Computing Decay Altitudes.")
     altDec, lenDec = eas.altDec(beta_tr, tauBeta, tauLorentz, valid_u("u_dec"), store=sw)
@@ -202,9 +211,8 @@ def _compute(config, verbose, output_file, to_plot, write_stages, seed, uniforms
         logv(f"\tNumber of Passing Events [Optical]: {passEV}")
         logv(f"\tStat uncert of MC Integral [Optical]: {mcunc}")
 
-    if output_file is not None and not write_stages:
-        sink.synchronize()
-        sim.write(output_file, format="fits", overwrite=True)
+    # like the reference, compute() itself writes only the staged files (write_stages); the
+    # final table is written by the caller (apps/run.py:209-210)
     return sim
 
 
@@ -235,6 +243,57 @@ def _gather_rank_sums(row):
     return np.stack([o.cpu().numpy() for o in out])
 
 
+def _host_columns(names, n):
+    """Full-length host arrays the slices' columns are copied into.
+
+    Page-locked when torch's caching host allocator already holds enough free page-locked
+    memory (a process that calls compute() repeatedly) or when there is no way to ask;
+    otherwise -- the first call of a process, i.e. the reference's `nuspacesim run` usage --
+    plain pageable memory: page-locking 1.2 GB takes ~1.6 s, copying into pageable memory
+    ~0.3 s.  In that case the pool is warmed in the background for the next call."""
+    torch = _lib.torch_cuda()
+    need = len(names) * n * 8
+    pinned = need <= PINNED_MAX_BYTES
+    if pinned and os.environ.get("NSS_HOST_COLUMNS", "auto") == "auto":
+        try:
+            st = torch.cuda.host_memory_stats()
+            free = st.get("reserved_bytes.current", 0) - st.get("allocated_bytes.current", 0)
+            pinned = free >= need
+        except Exception:
+            pinned = True
+        if not pinned:
+            _warm_pinned_pool(len(names), n)
+    elif os.environ.get("NSS_HOST_COLUMNS") == "pageable":
+        pinned = False
+    return {nm: torch.empty(n, dtype=torch.float64, pin_memory=pinned) for nm in names}
+
+
+_WARM_THREAD = None
+
+
+def _warm_pinned_pool(ncols, n):
+    """Allocate and release page-locked blocks of the result-column size on a helper thread so
+    that the NEXT compute() call finds them in torch's caching host allocator."""
+    global _WARM_THREAD
+    import threading
+
+    if _WARM_THREAD is not None and _WARM_THREAD.is_alive():
+        return
+    torch = _lib.torch_cuda()
+    dev = torch.cuda.current_device()
+
+    def work():
+        try:
+            torch.cuda.set_device(dev)
+            blocks = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(ncols)]
+            del blocks
+        except Exception:
+            pass
+
+    _WARM_THREAD = threading.Thread(target=work, name="nss-pinned-warm", daemon=True)
+    _WARM_THREAD.start()
+
+
 def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown, step,
                     first=0, last=None, shard=False):
     """compute() for large N: the same stage objects, called per slice of thrown events.
@@ -263,25 +322,30 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     logv(f"Computing thrown events [{first}, {last}) of {n_thrown} in {len(bounds)} pipelined "
          "slices.")
 
-    # uploads of every slice, in consumption order, on the side stream
-    pre = []
-    for lo, hi in bounds:
+    # uploads run PREFETCH_SLICES ahead of the slice being computed, in consumption order, on
+    # the side stream: the device never holds more than that many slices' uniforms
+    def upload(k):
+        lo, hi = bounds[k]
         d = {}
         if "u4" in U:
             d["u4"] = _lib.rows_to_device_prefetch(U["u4"], lo, hi)
         for name in ("u_spec", "u_tau", "u_dec", "u_profile"):
             if name in U:
                 d[name] = _lib.to_device_prefetch(U[name][lo:hi])
-        pre.append(d)
+        return d
+
+    pre = {k: upload(k) for k in range(min(PREFETCH_SLICES, len(bounds)))}
 
     names = [n for g in COLUMN_GROUPS for n in g]
-    host = {n: torch.empty(max(last - first, 1), dtype=torch.float64, pin_memory=True)
-            for n in names}
+    host = _host_columns(names, max(last - first, 1))
     WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2, "u_profile": 3}
     sums, off = [], 0
     thr = config.detector.optical.photo_electron_threshold
     mc_spec_norm = spec_weights_sum = 1.0
-    for (lo, hi), d in zip(bounds, pre):
+    for k, (lo, hi) in enumerate(bounds):
+        d = pre.pop(k)
+        if k + PREFETCH_SLICES < len(bounds):
+            pre[k + PREFETCH_SLICES] = upload(k + PREFETCH_SLICES)
         geom = RegionGeom(config, seed=seed)
         geom.first_event = lo
         thrown = hi - lo
@@ -308,7 +372,8 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
         cols["log_e_nu"], mc_spec_norm, spec_weights_sum = spec(
             nv, device=True, u=valid_u("u_spec"))
         (cols["tauBeta"], cols["tauLorentz"], cols["tauEnergy"], cols["showerEnergy"],
-         cols["tauExitProb"]) = tau(beta_tr, cols["log_e_nu"], u=valid_u("u_tau"))
+         cols["tauExitProb"]) = tau(beta_tr, cols["log_e_nu"], u=valid_u("u_tau"),
+                                    u_raw="u_tau" not in U)
         cols["altDec"], cols["lenDec"] = eas.altDec(beta_tr, cols["tauBeta"], cols["tauLorentz"],
                                                     valid_u("u_dec"))
         front = [n for n in names if n not in ("numPEs", "costhetaChEff")]
@@ -349,8 +414,6 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     logv(f"\tMonte Carlo Integral, GEO Only [Optical]: {mcintgeo}")
     logv(f"\tNumber of Passing Events [Optical]: {passEV}")
     logv(f"\tStat uncert of MC Integral [Optical]: {mcunc}")
-    if output_file is not None:
-        sim.write(output_file, format="fits", overwrite=True)
     return sim
 
 

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "../../include/nss_b200.h"
 #include "nss_eas_core.cuh"
 #include "nss_eas_tables.h"
@@ -34,6 +36,11 @@ struct Ops32 {
     return v;
   }
   static __device__ __forceinline__ double sum_d(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+  }
+  static __device__ __forceinline__ float sum_f(float v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
     return v;
@@ -140,6 +147,7 @@ eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long lo
     atomicAdd(&stats[4], st.JNe);
     atomicAdd(&stats[5], st.n_exp);
     atomicAdd(&stats[6], st.n_val_ne);
+    atomicAdd(&stats[7], st.reserved);
   }
 }
 
@@ -170,41 +178,34 @@ eas_finish_kernel(int mode, nss::EasParams P, const double* __restrict__ beta,
   }
 }
 
-bool g_tables_ready = false;
-int g_walk_blocks[2] = {0, 0};
-double* g_conex = nullptr;  // device copy of the CONEX Gaisser-Hillas table
+// Per-device lazily initialised state: the constant tables (one cudaMemcpyToSymbol per device,
+// a synchronous copy of 1.5 KB of HOST data, no device synchronisation) and the persistent
+// grid size of the two walk instantiations.  Guarded by a mutex so that concurrent first calls
+// from several host threads are safe; after that the entry points touch no shared state.
+constexpr int MAX_DEVICES = 64;
+std::mutex g_init_mutex;
+bool g_tables_ready[MAX_DEVICES] = {};
+int g_walk_blocks[MAX_DEVICES][2] = {};
+double* g_conex = nullptr;  // device copy of the CONEX Gaisser-Hillas table (registered)
 int g_conex_rows = 0;
 
-// per-process scratch (one process per GPU): prep + acc records and the work counter
-struct Scratch {
-  nss::EasPrep* prep = nullptr;
-  nss::EasAcc* acc = nullptr;
-  unsigned long long* counter = nullptr;
-  long long cap = 0;
-  int device = -1;
-} g_scr;
+inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-int scratch_reserve(long long n) {
-  int dev = 0;
-  cudaError_t err = cudaGetDevice(&dev);
-  if (err != cudaSuccess) return (int)err;
-  if (g_scr.device == dev && g_scr.cap >= n) return 0;
-  if (g_scr.prep) {
-    cudaDeviceSynchronize();
-    cudaFree(g_scr.prep);
-    cudaFree(g_scr.acc);
-    cudaFree(g_scr.counter);
-    g_scr = Scratch();
-    g_tables_ready = false;
-    g_walk_blocks[0] = g_walk_blocks[1] = 0;
-  }
-  long long cap = n < 4096 ? 4096 : n;
-  if ((err = cudaMalloc(&g_scr.prep, sizeof(nss::EasPrep) * cap)) != cudaSuccess) return (int)err;
-  if ((err = cudaMalloc(&g_scr.acc, sizeof(nss::EasAcc) * cap)) != cudaSuccess) return (int)err;
-  if ((err = cudaMalloc(&g_scr.counter, 256)) != cudaSuccess) return (int)err;
-  g_scr.cap = cap;
-  g_scr.device = dev;
-  return 0;
+// caller-supplied workspace of one launch: [work counter | EasPrep[n] | EasAcc[n]]
+struct Workspace {
+  unsigned long long* counter;
+  nss::EasPrep* prep;
+  nss::EasAcc* acc;
+};
+inline Workspace carve(void* ws, int64_t n) {
+  char* w = (char*)ws;
+  Workspace W;
+  W.counter = (unsigned long long*)w;
+  w += 256;
+  W.prep = (nss::EasPrep*)w;
+  w += align256((int64_t)sizeof(nss::EasPrep) * n);
+  W.acc = (nss::EasAcc*)w;
+  return W;
 }
 
 // optional per-launch CUDA-event timing of the walk kernel (nss_eas_profile_*)
@@ -216,38 +217,44 @@ int g_prof_n = 0, g_prof_cap = 0;
 int launch(int mode, const NssParams* p, const double* beta, const double* alt,
            const double* eshow, const uint8_t* mask, const double* u_profile,
            const double* cloud_ev, int64_t n, double* o0, double* o1, double* dph, double* cang,
-           unsigned long long* stats, void* stream) {
+           unsigned long long* stats, void* workspace, void* stream) {
   if (!p) return NSS_E_NULL;
   if (n < 0 || p->eas_profile < 0 || p->eas_profile > 2 || p->has_cloud < 0 || p->has_cloud > 2)
     return NSS_E_BADARG;
   if (n == 0) return 0;
-  if (!beta || !alt || !eshow || !o0 || !o1) return NSS_E_NULL;
+  if (!beta || !alt || !eshow || !o0 || !o1 || !workspace) return NSS_E_NULL;
   if (p->eas_profile == 2 && (!u_profile || !g_conex)) return NSS_E_NULL;
   if (p->has_cloud == 2 && !cloud_ev) return NSS_E_NULL;
   if (p->has_cloud != 2) cloud_ev = nullptr;
   const bool gh = p->eas_profile != 0;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t err;
-  int rc = scratch_reserve(n);
-  if (rc != 0) return rc;
-  if (!g_tables_ready) {
-    nss::EasTables T;
-    nss_eas_tables_init(&T);
-    err = cudaMemcpyToSymbol(c_tables, &T, sizeof(T));
-    if (err != cudaSuccess) return (int)err;
-    g_tables_ready = true;
+  int dev = 0;
+  if ((err = cudaGetDevice(&dev)) != cudaSuccess) return (int)err;
+  if (dev < 0 || dev >= MAX_DEVICES) return NSS_E_BADARG;
+  int walk_blocks;
+  {
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    if (!g_tables_ready[dev]) {
+      nss::EasTables T;
+      nss_eas_tables_init(&T);
+      err = cudaMemcpyToSymbol(c_tables, &T, sizeof(T));
+      if (err != cudaSuccess) return (int)err;
+      g_tables_ready[dev] = true;
+    }
+    if (g_walk_blocks[dev][gh] == 0) {
+      int sms = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      err = gh ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<true>,
+                                                               walk_block(true), 0)
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<false>,
+                                                               walk_block(false), 0);
+      if (err != cudaSuccess) return (int)err;
+      g_walk_blocks[dev][gh] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    walk_blocks = g_walk_blocks[dev][gh];
   }
-  if (g_walk_blocks[gh] == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = gh ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<true>,
-                                                             walk_block(true), 0)
-             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<false>,
-                                                             walk_block(false), 0);
-    if (err != cudaSuccess) return (int)err;
-    g_walk_blocks[gh] = sms * (per_sm > 0 ? per_sm : 1);
-  }
+  const Workspace W = carve(workspace, n);
   nss::EasParams P;
   P.detector_altitude = p->detector_altitude;
   P.area = p->telescope_effective_area;
@@ -261,15 +268,15 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
   const int tb = 256;
   long long g1 = (n + tb - 1) / tb;
   if (g1 > 148LL * 64) g1 = 148LL * 64;
-  err = cudaMemsetAsync(g_scr.counter, 0, 8, s);
+  err = cudaMemsetAsync(W.counter, 0, 8, s);
   if (err != cudaSuccess) return (int)err;
   eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, p->eas_profile, beta, alt, eshow, mask, g_conex,
                                          g_conex_rows, u_profile, cloud_ev, P.cloud_top, n,
-                                         g_scr.prep);
+                                         W.prep);
 
   const int wpb = walk_block(gh) / 32;  // warps (= events in flight) per block
   long long need = (n + wpb - 1) / wpb;
-  int blocks = (int)(need < g_walk_blocks[gh] ? need : g_walk_blocks[gh]);
+  int blocks = (int)(need < walk_blocks ? need : walk_blocks);
   ProfRec* rec = nullptr;
   if (g_profile) {
     if (g_prof_n == g_prof_cap) {
@@ -282,34 +289,41 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     cudaEventRecord(rec->a, s);
   }
   if (gh)
-    eas_walk_kernel<true><<<blocks, walk_block(true), 0, s>>>(P, g_scr.prep, n, g_scr.acc,
-                                                              g_scr.counter, stats);
+    eas_walk_kernel<true><<<blocks, walk_block(true), 0, s>>>(P, W.prep, n, W.acc, W.counter,
+                                                              stats);
   else
-    eas_walk_kernel<false><<<blocks, walk_block(false), 0, s>>>(P, g_scr.prep, n, g_scr.acc,
-                                                                g_scr.counter, stats);
+    eas_walk_kernel<false><<<blocks, walk_block(false), 0, s>>>(P, W.prep, n, W.acc, W.counter,
+                                                                stats);
   if (rec) cudaEventRecord(rec->b, s);
-  eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, g_scr.acc, g_scr.prep, n, o0, o1,
-                                           dph, cang);
+  eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, W.acc, W.prep, n, o0, o1, dph,
+                                           cang);
   return (int)cudaGetLastError();
 }
 
 }  // namespace
 
+extern "C" int64_t nss_eas_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  return 256 + align256((int64_t)sizeof(nss::EasPrep) * n) +
+         align256((int64_t)sizeof(nss::EasAcc) * n);
+}
+
 extern "C" int nss_eas_optical(const NssParams* p, const double* beta, const double* altDec,
                                const double* showerEnergy, const uint8_t* mask,
                                const double* u_profile, const double* cloud_top_ev, int64_t n,
                                double* numPEs, double* costhetaChEff, double* dphots,
-                               double* cang, unsigned long long* stats, void* stream) {
+                               double* cang, unsigned long long* stats, void* workspace,
+                               void* stream) {
   return launch(0, p, beta, altDec, showerEnergy, mask, u_profile, cloud_top_ev, n, numPEs,
-                costhetaChEff, dphots, cang, stats, stream);
+                costhetaChEff, dphots, cang, stats, workspace, stream);
 }
 
 extern "C" int nss_cphotang(const NssParams* p, const double* betaE, const double* alt,
                             const double* Eshow100PeV, const double* u_profile,
                             const double* cloud_top_ev, int64_t n, double* dphots, double* cang,
-                            unsigned long long* stats, void* stream) {
+                            unsigned long long* stats, void* workspace, void* stream) {
   return launch(1, p, betaE, alt, Eshow100PeV, nullptr, u_profile, cloud_top_ev, n, dphots,
-                cang, nullptr, nullptr, stats, stream);
+                cang, nullptr, nullptr, stats, workspace, stream);
 }
 
 extern "C" int nss_eas_set_conex_table(const double* rows_host, int nrows) {

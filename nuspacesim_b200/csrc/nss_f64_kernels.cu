@@ -317,6 +317,30 @@ compact_kernel(const uint8_t* __restrict__ mask, const int64_t* __restrict__ pos
     if (mask[i]) out[pos[i]] = (scale == 1.0) ? in[i] : in[i] * scale;
 }
 
+// the same for up to NSS_COMPACT_MAX_COLS columns in one pass: mask and pos are read once
+// per event instead of once per column (the accessors of one throw() all share them)
+struct CompactCols {
+  const double* in[NSS_COMPACT_MAX_COLS];
+  double* out[NSS_COMPACT_MAX_COLS];
+  double scale[NSS_COMPACT_MAX_COLS];
+  int ncols;
+};
+
+__global__ void __launch_bounds__(256)
+compact_columns_kernel(const uint8_t* __restrict__ mask, const int64_t* __restrict__ pos,
+                       CompactCols c, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    const int64_t o = pos[i];
+#pragma unroll 4
+    for (int k = 0; k < c.ncols; ++k) {
+      const double v = c.in[k][i];
+      c.out[k][o] = (c.scale[k] == 1.0) ? v : v * c.scale[k];
+    }
+  }
+}
+
 // uniform `which` (0 spectrum, 1 tau energy, 2 decay, 3 spare) of Philox stream 1 of every
 // valid thrown event, compacted in thrown order: the same words front_kernel consumes
 __global__ void __launch_bounds__(256)
@@ -409,8 +433,12 @@ __device__ inline double tau_exit_prob_event(const TabView& t, double beta, doub
 
 // z = E_tau / E_nu sampled from the bilinearly blended CDF row (cdf.py:373-425,
 // interp.py:126-146): locate the single crossing cdf[k-1] < u <= cdf[k], lerp the axis.
+// raw: u is a plain (0, 1) draw and is mapped onto (cdf[0], 1) of the event's blended row,
+// u' = c0 + (1 - c0) u -- the reference's own draw np.random.uniform(cdfs[:, 0], 1.0)
+// (cdf.py:419-423; c0 = 0 for the nupyprop tables, up to 0.0134 for nuleptonsim).  A
+// caller-supplied u (raw = false) is used as it is, like the reference's `u` argument.
 __device__ inline double tau_z_event(const TabView& t, double beta, double loge, double u,
-                                     int32_t* flags) {
+                                     bool raw, int32_t* flags) {
   const double bmin = t.cdf_beta[0], bmax = t.cdf_beta[t.nB2 - 1];
   if (!(loge >= t.cdf_loge[0] && loge <= t.cdf_loge[t.nE2 - 1])) {
     if (flags) atomicOr(flags, NSS_FLAG_LOGE_RANGE);
@@ -430,6 +458,7 @@ __device__ inline double tau_z_event(const TabView& t, double beta, double loge,
   const double w00 = (1 - we) * (1 - wb), w01 = (1 - we) * wb, w10 = we * (1 - wb), w11 = we * wb;
   auto row = [&](int k) { return r00[k] * w00 + r01[k] * w01 + r10[k] * w10 + r11[k] * w11; };
   double c_lo = row(0), c_hi = row(nZ - 1);
+  if (raw) u = c_lo + (1.0 - c_lo) * u;
   if (!(c_lo < u) || !(c_hi >= u)) {
     if (flags) atomicOr(flags, NSS_FLAG_U_RANGE);
     return nan("");
@@ -450,10 +479,10 @@ struct TauOut {
 };
 
 __device__ inline void tau_event(const NssParams& p, const TabView& t, double beta, double loge,
-                                 double u, int32_t* flags, TauOut& o) {
+                                 double u, bool raw, int32_t* flags, TauOut& o) {
   // taus.py:154-183
   o.tauExitProb = tau_exit_prob_event(t, beta, loge, flags);
-  const double z = tau_z_event(t, beta, loge, u, flags);
+  const double z = tau_z_event(t, beta, loge, u, raw, flags);
   o.tauEnergy = z * pow(10.0, loge);
   o.showerEnergy = p.etau_frac * o.tauEnergy / 1e8;
   o.tauLorentz = o.tauEnergy / MASS_TAU;
@@ -471,16 +500,16 @@ __device__ inline void alt_dec_event(double R, double beta, double tauBeta, doub
 __global__ void __launch_bounds__(256)
 tau_kernel(NssParams p, TabView t, const double* __restrict__ beta, const double* __restrict__ le,
            const double* __restrict__ u, int64_t n, double* tb, double* tl, double* te, double* sh,
-           double* pex, int32_t* flags, int what) {
+           double* pex, int32_t* flags, int what, bool raw) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     if (what == 1) {
       pex[i] = tau_exit_prob_event(t, beta[i], le[i], flags);
     } else if (what == 2) {
-      te[i] = tau_z_event(t, beta[i], le[i], u[i], flags) * pow(10.0, le[i]);
+      te[i] = tau_z_event(t, beta[i], le[i], u[i], raw, flags) * pow(10.0, le[i]);
     } else {
       TauOut o;
-      tau_event(p, t, beta[i], le[i], u[i], flags, o);
+      tau_event(p, t, beta[i], le[i], u[i], raw, flags, o);
       if (tb) tb[i] = o.tauBeta;
       if (tl) tl[i] = o.tauLorentz;
       if (te) te[i] = o.tauEnergy;
@@ -628,7 +657,7 @@ front_kernel(NssParams p, TabView t, CloudMapView cm, uint64_t seed, uint64_t fi
     const double beta = g.betaTrSubN * (PI_D / 180.0);
     const double le = p.spectrum_kind == 0 ? p.log_nu_energy : powerlaw_log_e(p, u01(w1[0]));
     TauOut to;
-    tau_event(p, t, beta, le, u01(w1[1]), flags, to);
+    tau_event(p, t, beta, le, u01(w1[1]), true, flags, to);
     double alt, len;
     alt_dec_event(p.earth_radius, beta, to.tauBeta, to.tauLorentz, u01(w1[2]), alt, len);
     b.beta[i] = beta;
@@ -824,6 +853,25 @@ extern "C" int nss_compact_f64(const uint8_t* mask, const int64_t* pos, const do
   return (int)cudaGetLastError();
 }
 
+extern "C" int nss_compact_columns_f64(const uint8_t* mask, const int64_t* pos,
+                                       const double* const* in, double* const* out,
+                                       const int* to_radians, int ncols, int64_t n,
+                                       void* stream) {
+  if (n < 0 || ncols < 0 || ncols > NSS_COMPACT_MAX_COLS) return NSS_E_BADARG;
+  if (n == 0 || ncols == 0) return 0;
+  if (!mask || !pos || !in || !out) return NSS_E_NULL;
+  CompactCols c;
+  c.ncols = ncols;
+  for (int k = 0; k < ncols; ++k) {
+    if (!in[k] || !out[k]) return NSS_E_NULL;
+    c.in[k] = in[k];
+    c.out[k] = out[k];
+    c.scale[k] = (to_radians && to_radians[k]) ? PI_D / 180.0 : 1.0;
+  }
+  compact_columns_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, pos, c, n);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int nss_event_uniforms(uint64_t seed, uint64_t first_event, int64_t n,
                                   const uint8_t* mask, const int64_t* pos, int which,
                                   double* out, void* stream) {
@@ -862,7 +910,7 @@ extern "C" int nss_spectrum_powerlaw(const NssParams* p, const double* u, int64_
 
 static int tau_launch(const NssParams* p, const NssTables* t, const double* b, const double* le,
                       const double* u, int64_t n, double* tb, double* tl, double* te, double* sh,
-                      double* pex, int32_t* flags, int what, void* stream) {
+                      double* pex, int32_t* flags, int what, int u_raw, void* stream) {
   if (!t) return NSS_E_NULL;
   if (n < 0) return NSS_E_BADARG;
   if (n == 0) return 0;
@@ -871,7 +919,8 @@ static int tau_launch(const NssParams* p, const NssTables* t, const double* b, c
   memset(&pp, 0, sizeof(pp));
   if (p) pp = *p;
   tau_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pp, view_of(t), b, le, u, n, tb,
-                                                                 tl, te, sh, pex, flags, what);
+                                                                 tl, te, sh, pex, flags, what,
+                                                                 u_raw != 0);
   return (int)cudaGetLastError();
 }
 
@@ -879,25 +928,26 @@ extern "C" int nss_tau_exit_prob(const NssTables* t, const double* betas, const 
                                  int64_t n, double* pexit, int32_t* flags, void* stream) {
   if (n > 0 && !pexit) return NSS_E_NULL;
   return tau_launch(nullptr, t, betas, log_e_nu, nullptr, n, nullptr, nullptr, nullptr, nullptr,
-                    pexit, flags, 1, stream);
+                    pexit, flags, 1, 0, stream);
 }
 
 extern "C" int nss_tau_energy(const NssTables* t, const double* betas, const double* log_e_nu,
-                              const double* u, int64_t n, double* tau_energy, int32_t* flags,
-                              void* stream) {
+                              const double* u, int u_raw, int64_t n, double* tau_energy,
+                              int32_t* flags, void* stream) {
   if (n > 0 && (!tau_energy || !u)) return NSS_E_NULL;
   return tau_launch(nullptr, t, betas, log_e_nu, u, n, nullptr, nullptr, tau_energy, nullptr,
-                    nullptr, flags, 2, stream);
+                    nullptr, flags, 2, u_raw, stream);
 }
 
 extern "C" int nss_tau_sample(const NssParams* p, const NssTables* t, const double* betas,
-                              const double* log_e_nu, const double* u, int64_t n, double* tauBeta,
-                              double* tauLorentz, double* tauEnergy, double* showerEnergy,
-                              double* tauExitProb, int32_t* flags, void* stream) {
+                              const double* log_e_nu, const double* u, int u_raw, int64_t n,
+                              double* tauBeta, double* tauLorentz, double* tauEnergy,
+                              double* showerEnergy, double* tauExitProb, int32_t* flags,
+                              void* stream) {
   if (!p) return NSS_E_NULL;
   if (n > 0 && !u) return NSS_E_NULL;
   return tau_launch(p, t, betas, log_e_nu, u, n, tauBeta, tauLorentz, tauEnergy, showerEnergy,
-                    tauExitProb, flags, 0, stream);
+                    tauExitProb, flags, 0, u_raw, stream);
 }
 
 extern "C" int nss_alt_dec(const double* beta, const double* tauBeta, const double* tauLorentz,
@@ -983,7 +1033,8 @@ extern "C" int nss_cloud_top_from_map(const double* lat, const double* lon, int6
 
 extern "C" int64_t nss_acceptance_workspace_bytes(int64_t batch) {
   if (batch <= 0) return 0;
-  return 10 * align256(batch * 8) + align256(batch) + align256((int64_t)MC_GRID * MC_NSUM * 8);
+  return 10 * align256(batch * 8) + align256(batch) + align256((int64_t)MC_GRID * MC_NSUM * 8) +
+         nss_eas_workspace_bytes(batch);
 }
 
 extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64_t seed,
@@ -1005,6 +1056,8 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
   b.mask = (uint8_t*)w;
   w += align256(batch);
   double* partial = (double*)w;
+  w += align256((int64_t)MC_GRID * MC_NSUM * 8);
+  void* eas_ws = (void*)w;
   double sn, sw;
   spec_norms(p, sn, sw);
   TabView tv = view_of(t);
@@ -1015,7 +1068,7 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
     int rc = nss_eas_optical(p, b.beta, b.alt, b.shower, b.mask,
                              p->eas_profile == 2 ? b.uprof : nullptr,
                              p->has_cloud == 2 ? b.cloud : nullptr, m, b.npe, b.cth, nullptr,
-                             nullptr, stats, stream);
+                             nullptr, stats, eas_ws, stream);
     if (rc != 0) return rc;
     int grid = (int)((m + MC_BLOCK - 1) / MC_BLOCK < MC_GRID ? (m + MC_BLOCK - 1) / MC_BLOCK
                                                              : MC_GRID);

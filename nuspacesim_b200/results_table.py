@@ -111,37 +111,41 @@ def output_filename(filename=None, now=None) -> str:
 # ------------------------------------------------------------------ minimal FITS
 
 
-def _fmt_value(v) -> str:
+def _fmt_value(v, room: int = 68) -> str:
+    """FITS value field; a string is cut so that it still closes its quote within `room`."""
     if isinstance(v, (bool, np.bool_)):
         return "T" if v else "F"
     if isinstance(v, (int, np.integer)):
         return str(int(v))
-    if isinstance(v, (float, np.floating)):
-        if not np.isfinite(v):
-            return "'" + str(v) + "'"
+    if isinstance(v, (float, np.floating)) and np.isfinite(v):
         s = repr(float(v)).upper()
         return s if ("." in s or "E" in s) else s + ".0"
-    s = str(v).replace("'", "''")
-    return "'" + s + "'"
+    s = "".join(ch if " " <= ch <= "~" else "?" for ch in str(v)).replace("'", "''")
+    s = s[:max(room - 2, 0)]
+    if s.endswith("'") and (len(s) - len(s.rstrip("'"))) % 2:  # do not split an escaped quote
+        s = s[:-1]
+    return "'" + f"{s:<8}" + "'"
 
 
 def _card(key: str, value=None, comment: str = "") -> bytes:
+    """One 80-character header card (FITS 4.0 sec. 4.1-4.2).  Keywords of up to 8 characters
+    are written upper-case, like astropy writes the reference's ``simTime`` meta key as
+    ``SIMTIME`` (results_table.py:60-66); longer or blank-containing keys use the ESO
+    HIERARCH convention astropy uses for ``HIERARCH Config ...``."""
     if value is None:
         text = key
     elif key.startswith("HIERARCH ") or len(key) > 8 or " " in key:
         k = key if key.startswith("HIERARCH ") else "HIERARCH " + key
-        text = f"{k} = {_fmt_value(value)}"
+        head = f"{k} = "
+        text = head + _fmt_value(value, 80 - len(head))
         if comment and len(text) + 3 + len(comment) <= 80:
             text += " / " + comment
     else:
         val = _fmt_value(value)
-        if val.startswith("'"):
-            val = f"{val:<20}"
-        else:
-            val = f"{val:>20}"
-        text = f"{key:<8}= {val}"
-        if comment:
-            text += " / " + comment
+        val = f"{val:<20}" if val.startswith("'") else f"{val:>20}"
+        text = f"{key.upper():<8}= {val}"
+        if comment and len(text) + 3 < 80:
+            text += " / " + "".join(ch if " " <= ch <= "~" else "?" for ch in comment)
     return text[:80].ljust(80).encode("ascii", "replace")
 
 

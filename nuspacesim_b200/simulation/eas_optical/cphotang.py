@@ -111,10 +111,11 @@ class CphotAng:
             cloudf, init_lat, init_long, n)
         d, c = _lib.empty(n), _lib.empty(n)
         up = self.profile_uniforms(n, u_profile)
+        ws = _lib.eas_workspace(n)
         _lib.check(
             _lib.lib().nss_cphotang(C.byref(self.params), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e),
                                     _lib.ptr(up), _lib.ptr(ctops), n, _lib.ptr(d), _lib.ptr(c),
-                                    _lib.ptr(stats), _lib.stream_ptr()),
+                                    _lib.ptr(stats), _lib.ptr(ws), _lib.stream_ptr()),
             "nss_cphotang",
         )
         return (d, c) if dev else (_lib.to_host(d), _lib.to_host(c))

@@ -65,11 +65,12 @@ class EAS:
         p.has_cloud, p.cloud_top, ctops = cloud_args(cloudf, init_lat, init_long, n)
         npe, cth = _lib.empty(n), _lib.empty(n)
         up = self.CphotAng.profile_uniforms(n, u_profile)
+        ws = _lib.eas_workspace(n)
         _lib.check(
             _lib.lib().nss_eas_optical(C.byref(p), _lib.ptr(b), _lib.ptr(a), _lib.ptr(e), None,
                                        _lib.ptr(up), _lib.ptr(ctops), n, _lib.ptr(npe),
                                        _lib.ptr(cth), None, None,
-                                       _lib.ptr(self.stats), _lib.stream_ptr()),
+                                       _lib.ptr(self.stats), _lib.ptr(ws), _lib.stream_ptr()),
             "nss_eas_optical",
         )
         return (npe, cth) if dev else (_lib.to_host(npe), _lib.to_host(cth))

@@ -112,6 +112,8 @@ class RegionGeom:
         if f.numel() != self._n:
             raise RuntimeError(f"expected one entry per thrown event ({self._n}), got {f.numel()}")
         out = _lib.empty(self._n_valid)
+        if self._n_valid == 0:  # nothing to move (and an empty tensor has no address to pass)
+            return out if device else _lib.to_host(out)
         _lib.check(
             _lib.lib().nss_compact_f64(
                 _lib.ptr(self._dev["event_mask"]), _lib.ptr(self._pos), _lib.ptr(f),
@@ -144,18 +146,35 @@ class RegionGeom:
 
     # ------------------------------------------------------------------ accessors (:241-287)
 
+    #: the accessors compute() uses on every throw: compacted together, in ONE launch, the
+    #: first time any of them is asked for (mask and positions are read once, not 13 times)
+    _COMMON = (("betaTrSubN", True), ("thetaTrSubV", False), ("losPathLen", False),
+               ("phiTrSubV", False), ("elevAngVSubN", False), ("aziAngVSubN", False),
+               ("longS", False), ("latS", False), ("costhetaTrSubN", False),
+               ("costhetaNSubV", False), ("costhetaTrSubV", False))
+
+    def _compact_many(self, keys):
+        keys = [k for k in keys if k not in self._valid_cache]
+        outs = [_lib.empty(self._n_valid) for _ in keys]
+        if self._n_valid and keys:
+            # a slice or rank shard with no valid event yields empty columns (compute.py:200-204)
+            k = len(keys)
+            ins = (C.c_void_p * k)(*[self._dev[name].data_ptr() for name, _ in keys])
+            dst = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
+            rad = (C.c_int * k)(*[int(r) for _, r in keys])
+            _lib.check(
+                _lib.lib().nss_compact_columns_f64(
+                    _lib.ptr(self._dev["event_mask"]), _lib.ptr(self._pos), ins, dst, rad, k,
+                    self._n, _lib.stream_ptr()),
+                "nss_compact_columns_f64",
+            )
+        for key, o in zip(keys, outs):
+            self._valid_cache[key] = o
+
     def _valid(self, name, to_radians=False, device=False):
         key = (name, to_radians)
         if key not in self._valid_cache:
-            out = _lib.empty(self._n_valid)
-            _lib.check(
-                _lib.lib().nss_compact_f64(
-                    _lib.ptr(self._dev["event_mask"]), _lib.ptr(self._pos),
-                    _lib.ptr(self._dev[name]), _lib.ptr(out), self._n, int(to_radians),
-                    _lib.stream_ptr()),
-                "nss_compact_f64",
-            )
-            self._valid_cache[key] = out
+            self._compact_many(self._COMMON if key in self._COMMON else (key,))
         t = self._valid_cache[key]
         return t if device else _lib.to_host(t)
 

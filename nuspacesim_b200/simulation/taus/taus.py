@@ -124,11 +124,16 @@ class Taus:
             raise RuntimeError(f"Input Array Shape Mismatch: {tuple(le.shape)}, {tuple(b.shape)}")
         return b, le, dev
 
-    def _uniform(self, n, u):
+    def _uniform(self, n, u, u_raw):
+        """-> (device uniforms, raw flag).  Uniforms drawn here are plain (0, 1) draws that the
+        kernel maps onto (cdf[0], 1) of each event's blended CDF row, like the reference's
+        np.random.uniform(cdfs[:, 0], 1.0) (utils/cdf.py:419-423); a caller's ``u`` is used as
+        it is unless ``u_raw`` says it is such a plain draw too."""
         if u is None:
             # open interval (0, 1): u == cdf[0] breaks the crossing search (SURVEY 7.3.5)
             u = (self._rng.integers(0, 2**53, size=n).astype(np.float64) + 0.5) / 2.0**53
-        return _lib.to_device(u)
+            u_raw = True
+        return _lib.to_device(u), int(bool(u_raw))
 
     def tau_exit_prob(self, betas, log_e_nu):
         """Tau Exit Probability (taus.py:99-122)."""
@@ -142,15 +147,16 @@ class Taus:
         self._check_flags(flags)
         return out if dev else _lib.to_host(out)
 
-    def tau_energy(self, betas, log_e_nu, u=None):
+    def tau_energy(self, betas, log_e_nu, u=None, u_raw=False):
         """Tau energies sampled from the interpolated CDF (taus.py:124-146).
 
-        ``u`` holds one uniform per event (event i consumes u[i])."""
+        ``u`` holds one uniform per event (event i consumes u[i]); ``u_raw`` (extension): the
+        given ``u`` are plain (0, 1) draws to be mapped onto (cdf[0], 1) per event."""
         b, le, dev = self._inputs(betas, log_e_nu)
-        ud = self._uniform(b.numel(), u)
+        ud, raw = self._uniform(b.numel(), u, u_raw)
         out, flags = _lib.empty(b.numel()), _lib.zeros(1, "int32")
         _lib.check(
-            _lib.lib().nss_tau_energy(self.tables, _lib.ptr(b), _lib.ptr(le), _lib.ptr(ud),
+            _lib.lib().nss_tau_energy(self.tables, _lib.ptr(b), _lib.ptr(le), _lib.ptr(ud), raw,
                                       b.numel(), _lib.ptr(out), _lib.ptr(flags),
                                       _lib.stream_ptr()),
             "nss_tau_energy",
@@ -162,16 +168,17 @@ class Taus:
     @decorators.nss_result_store(
         "tauBeta", "tauLorentz", "tauEnergy", "showerEnergy", "tauExitProb"
     )
-    def __call__(self, betas, log_e_nu, *args, u=None, **kwargs):
+    def __call__(self, betas, log_e_nu, *args, u=None, u_raw=False, **kwargs):
         """taus.py:154-183 -> (tauBeta, tauLorentz, tauEnergy, showerEnergy, tauExitProb)."""
         b, le, dev = self._inputs(betas, log_e_nu)
         n = b.numel()
-        ud = self._uniform(n, u)
+        ud, raw = self._uniform(n, u, u_raw)
         outs = [_lib.empty(n) for _ in range(5)]
         flags = _lib.zeros(1, "int32")
         _lib.check(
             _lib.lib().nss_tau_sample(C.byref(self.params), self.tables, _lib.ptr(b),
-                                      _lib.ptr(le), _lib.ptr(ud), n, *[_lib.ptr(o) for o in outs],
+                                      _lib.ptr(le), _lib.ptr(ud), raw, n,
+                                      *[_lib.ptr(o) for o in outs],
                                       _lib.ptr(flags), _lib.stream_ptr()),
             "nss_tau_sample",
         )

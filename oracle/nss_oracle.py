@@ -270,8 +270,11 @@ def tau_exit_prob(pexit: np.ndarray, ax_le: np.ndarray, ax_b: np.ndarray, betas,
     return 10**v
 
 
-def cdf_sample(cdf: np.ndarray, ax_le, ax_b, ax_z, log_e_nu, beta, u):
-    """cdf.py:373-425 + interp.py:126-146 with explicit ``u`` (one per event)."""
+def cdf_sample(cdf: np.ndarray, ax_le, ax_b, ax_z, log_e_nu, beta, u, u_raw=False):
+    """cdf.py:373-425 + interp.py:126-146 with explicit ``u`` (one per event).  ``u_raw``: the
+    given u are plain (0, 1) draws and are mapped onto (cdf[0], 1) of each event's blended row,
+    low + (high - low) u, which is how the reference's own draw
+    ``np.random.uniform(cdfs[:, 0], 1.0)`` (cdf.py:419-423) uses its generator's output."""
     log_e_nu = np.asarray(log_e_nu, dtype=np.float64)
     beta = np.asarray(beta, dtype=np.float64)
     u = np.asarray(u, dtype=np.float64)
@@ -292,6 +295,8 @@ def cdf_sample(cdf: np.ndarray, ax_le, ax_b, ax_z, log_e_nu, beta, u):
         rows = (cdf[i, j] * ((1 - a) * (1 - c)) + cdf[i, j + 1] * ((1 - a) * c)
                 + cdf[i + 1, j] * (a * (1 - c)) + cdf[i + 1, j + 1] * (a * c))
         x = u[sl]
+        if u_raw:
+            x = rows[:, 0] + (1.0 - rows[:, 0]) * x
         # vec_1d_interp: "lo" = first knot >= x, "hi" = last knot < x (names as in
         # the reference, which swaps them; the lerp is written from the upper knot)
         k_up = np.argmax(rows >= x[:, None], axis=1)
@@ -305,7 +310,7 @@ def cdf_sample(cdf: np.ndarray, ax_le, ax_b, ax_z, log_e_nu, beta, u):
     return out
 
 
-def tau_energy(cdf, ax_le, ax_b, ax_z, betas, log_e_nu, u):
+def tau_energy(cdf, ax_le, ax_b, ax_z, betas, log_e_nu, u, u_raw=False):
     """taus.py:124-146; ``u`` is one uniform per event (the reference's own
     ``u`` plumbing is broken when any beta < beta_min -- SURVEY 7.3 item 6 -- so
     the per-event meaning is used: event i consumes u[i])."""
@@ -313,17 +318,17 @@ def tau_energy(cdf, ax_le, ax_b, ax_z, betas, log_e_nu, u):
     log_e_nu = np.asarray(log_e_nu, dtype=np.float64)
     lo, hi = betas < ax_b[0], betas > ax_b[-1]
     bb = np.where(lo, ax_b[0], np.where(hi, ax_b[-1], betas))
-    z = cdf_sample(cdf, ax_le, ax_b, ax_z, log_e_nu, bb, u)
+    z = cdf_sample(cdf, ax_le, ax_b, ax_z, log_e_nu, bb, u, u_raw)
     z = np.where(hi, F32_EPS, z)
     return z * (10**log_e_nu)
 
 
-def taus(p: OracleParams, tables, betas, log_e_nu, u):
+def taus(p: OracleParams, tables, betas, log_e_nu, u, u_raw=False):
     """taus.py:154-183 -> (tauBeta, tauLorentz, tauEnergy, showerEnergy, tauExitProb)."""
     pex = tau_exit_prob(tables["pexit"], tables["pexit_log_e_nu"], tables["pexit_beta_rad"],
                         betas, log_e_nu)
     te = tau_energy(tables["cdf"], tables["cdf_log_e_nu"], tables["cdf_beta_rad"],
-                    tables["cdf_e_tau_frac"], betas, log_e_nu, u)
+                    tables["cdf_e_tau_frac"], betas, log_e_nu, u, u_raw)
     shower = p.etau_frac * te / 1e8
     lor = te / MASS_TAU
     with np.errstate(invalid="ignore"):
@@ -584,7 +589,7 @@ def eas(p: OracleParams, beta, altDec, showerEnergy, nthreads=1, gh_rows=None, c
 
 
 def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1, u_profile=None,
-             conex=None):
+             conex=None, u_tau_raw=False):
     """compute.py:186-257 (optical branch) on pre-sampled uniforms.
 
     For "Gaisser-Hillas Fluctuated", ``u_profile`` (length N, by thrown event) picks the row
@@ -600,7 +605,7 @@ def run_path(p: OracleParams, tables, u4, u_spec, u_tau, u_dec, nthreads=1, u_pr
     m = t["event_mask"]
     beta = np.radians(t["betaTrSubN"][m])
     le, sn, sw = spectra(p, int(m.sum()), None if u_spec is None else np.asarray(u_spec)[m])
-    tb, lor, te, sh, pex = taus(p, tables, beta, le, np.asarray(u_tau)[m])
+    tb, lor, te, sh, pex = taus(p, tables, beta, le, np.asarray(u_tau)[m], u_tau_raw)
     alt, length = alt_dec(beta, tb, lor, np.asarray(u_dec)[m])
     rows = None
     if PROFILES[getattr(p, "eas_long_profile", "Greisen")] == 2:

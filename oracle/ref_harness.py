@@ -38,14 +38,79 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("NSS_REFERENCE_ROOT", "/root/reference")
-REF_SRC = os.path.join(REF_ROOT, "src", "nuspacesim")
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BUILD = os.path.join(HERE, "_ref")
+#: archive of the reference files the path needs, made by stage_reference() at build time so
+#: that the reference itself can be TIMED on the GPU box's host cores (bench.py --impl
+#: reference); oracle/_ref/ is git-ignored build output, like the compiled zsteps next to it
+REF_STAGED_TAR = os.path.join(REF_BUILD, "reference_staged.tar.gz")
+LIVE_ROOT = os.environ.get("NSS_REFERENCE_ROOT", "/root/reference")
+
+
+def _unpack_staged() -> str:
+    """The staged archive is unpacked into a scratch directory outside the repository each
+    time it is needed (nothing of the reference lies unpacked in the tree)."""
+    import tarfile
+    import tempfile
+
+    dst = os.path.join(tempfile.gettempdir(), f"nss_reference_{os.getuid()}_{os.getpid()}")
+    if not os.path.isdir(os.path.join(dst, "src", "nuspacesim")):
+        with tarfile.open(REF_STAGED_TAR) as tf:
+            tf.extractall(dst)
+        import atexit
+        import shutil
+
+        atexit.register(shutil.rmtree, dst, True)
+    return dst
+
+
+if os.path.isdir(os.path.join(LIVE_ROOT, "src", "nuspacesim")):
+    REF_ROOT = LIVE_ROOT
+elif os.path.exists(REF_STAGED_TAR):
+    REF_ROOT = _unpack_staged()
+else:
+    REF_ROOT = LIVE_ROOT
+REF_SRC = os.path.join(REF_ROOT, "src", "nuspacesim")
 
 
 def reference_available() -> bool:
+    """The live tree (/root/reference, build container) or the staged copy (GPU box)."""
     return os.path.isdir(REF_SRC)
+
+
+def reference_is_live() -> bool:
+    return REF_ROOT == LIVE_ROOT and os.path.isdir(REF_SRC)
+
+
+def stage_reference() -> str:
+    """Copy, UNMODIFIED, exactly the reference files load_reference() imports, plus zsteps.cpp,
+    sample_input_file.toml and the default nu2tau tables, from the live tree into
+    one archive, oracle/_ref/reference_staged.tar.gz (same relative paths).  Called by
+    __graft_entry__.build() where /root/reference exists; the archive travels to the GPU box
+    with the other build outputs and is unpacked into a scratch directory when used."""
+    import io
+    import tarfile
+
+    if not reference_is_live():
+        raise RuntimeError("stage_reference() needs the live reference tree")
+    load_reference()
+    files = {"sample_input_file.toml",
+             "src/nuspacesim/simulation/eas_optical/src/zsteps.cpp",
+             "src/nuspacesim/data/nupyprop_tables/nu2tau_pexit.3.h5",
+             "src/nuspacesim/data/nupyprop_tables/nu2tau_cdf.3.h5"}
+    for m in list(sys.modules.values()):
+        f = getattr(m, "__file__", None)
+        if f and os.path.abspath(f).startswith(os.path.abspath(LIVE_ROOT) + os.sep):
+            files.add(os.path.relpath(os.path.abspath(f), LIVE_ROOT))
+    os.makedirs(REF_BUILD, exist_ok=True)
+    with tarfile.open(REF_STAGED_TAR, "w:gz") as tf:
+        for rel in sorted(files):
+            tf.add(os.path.join(LIVE_ROOT, rel), arcname=rel)
+        listing = ("\n".join(sorted(files)) + "\n").encode()
+        info = tarfile.TarInfo("STAGED_FILES.txt")
+        info.size = len(listing)
+        tf.addfile(info, io.BytesIO(listing))
+    return REF_STAGED_TAR
 
 
 # ----------------------------------------------------------------- zsteps build
@@ -72,6 +137,15 @@ def build_zsteps(force: bool = False) -> str:
 
 
 # ----------------------------------------------------------------- stubs
+
+#: worker processes of the dask.bag stand-in (1 = sequential); set by oracle/ref_bench.py
+POOL_SIZE = 1
+_BAG_F = None
+
+
+def _bag_call(x):
+    return _BAG_F(x)
+
 
 
 class _Unit:
@@ -218,17 +292,29 @@ def _install_stubs():
     bag = types.ModuleType("dask.bag")
 
     class _Bag:
-        def __init__(self, seq):
-            self.seq, self.f = list(seq), None
+        """dask.bag's default scheduler is a process pool over partitions of the sequence
+        (cphotang.py:719-723); POOL_SIZE > 1 reproduces that with multiprocessing (fork: the
+        mapped lambda and the CphotAng instance are inherited, only the event tuples and the
+        results are pickled, as with dask)."""
+
+        def __init__(self, seq, partition_size=None):
+            self.seq, self.f, self.part = list(seq), None, partition_size or 100
 
         def map(self, f):
             self.f = f
             return self
 
         def compute(self):
-            return [self.f(x) for x in self.seq]
+            global _BAG_F
+            if POOL_SIZE <= 1 or len(self.seq) < 2 * self.part:
+                return [self.f(x) for x in self.seq]
+            import multiprocessing as mp
 
-    bag.from_sequence = lambda seq, partition_size=None: _Bag(seq)
+            _BAG_F = self.f
+            with mp.get_context("fork").Pool(POOL_SIZE) as pool:
+                return pool.map(_bag_call, self.seq, chunksize=self.part)
+
+    bag.from_sequence = lambda seq, partition_size=None: _Bag(seq, partition_size)
     diag = types.ModuleType("dask.diagnostics")
     diag.__path__ = []
     prog = types.ModuleType("dask.diagnostics.progress")

@@ -101,6 +101,37 @@ def test_geometry_errors_and_edges(nss):
     assert np.array_equal(g2.event_mask, g3.event_mask)
 
 
+def test_no_valid_events_yields_empty_results(nss, capsys):
+    """Thrown events that are ALL masked out (compute.py:200-204: 'No valid events thrown'):
+    empty columns, no error -- for the accessors, the one-shot and the sliced pipeline."""
+    cfg = make_config(max_ch=np.radians(20.0))
+    p = O.OracleParams(max_cherenkov_angle=np.radians(20.0))
+    rng = np.random.default_rng(11)
+    u = rng.random((4, 4000))
+    bad = ~O.geom_throw(O.geom_constants(p), u)["event_mask"]
+    assert bad.sum() >= 3
+    u_bad = np.ascontiguousarray(u[:, bad][:, :3])
+    g = nss.RegionGeom(cfg)
+    b, t, pl = g(u_bad)
+    assert b.size == t.size == pl.size == 0 and not g.event_mask.any()
+    assert g.compact(np.arange(3.0), device=False).size == 0
+    lat, lon = g.find_lat_long_along_traj(np.zeros(0))
+    assert lat.size == lon.size == 0
+    U = dict(u4=u_bad, u_tau=np.full(3, 0.5), u_dec=np.full(3, 0.5))
+    sim = nss.compute(cfg, uniforms=U)
+    assert len(sim) == 0
+    assert "No valid events" in capsys.readouterr().out
+    # a slice without valid events between slices that have some
+    u_mix = np.ascontiguousarray(np.concatenate([u[:, :5], u_bad, u[:, 5:9]], axis=1))
+    n = u_mix.shape[1]
+    Um = dict(u4=u_mix, u_tau=np.full(n, 0.5), u_dec=np.full(n, 0.5))
+    one = nss.compute(cfg, uniforms=Um, slice_events=0)
+    sliced = nss.compute(cfg, uniforms=Um, slice_events=1)  # events 5, 6, 7 are empty slices
+    assert 0 < len(one) == len(sliced)
+    for c in one.colnames:
+        assert np.array_equal(np.asarray(one[c]), np.asarray(sliced[c]), equal_nan=True), c
+
+
 @pytest.mark.parametrize("tag", list(TAU_TABLES))
 def test_taus_vs_reference(nss, golden, tag):
     tg = golden["taus"]
@@ -137,6 +168,36 @@ def test_taus_errors_and_sampling(nss):
     z = e / 10**loge
     assert not np.isnan(z).any() and not np.all(z == 0) and not np.all(z == 1)
     assert z.min() >= t.tau_cdf_grid["e_tau_frac"][0] and z.max() <= 1.0 + 1e-12
+
+
+@pytest.mark.parametrize("tag", ["nls0", "np3"])
+def test_tau_energy_raw_uniforms(nss, tag):
+    """Uniforms the path draws itself (host generator or Philox) are mapped onto (cdf[0], 1) of
+    each event's blended CDF row like the reference's np.random.uniform(cdfs[:, 0], 1.0)
+    (utils/cdf.py:419-423): bit-level agreement with the reference run on the same generator
+    outputs (tests/golden/make_golden_taus_raw.py), also where the nuleptonsim CDF starts at
+    0.0134; compute() on that table at high energy no longer leaves the table."""
+    import os
+
+    from conftest import GOLDEN
+
+    G = np.load(os.path.join(GOLDEN, "taus_raw.npz"))
+    t = nss.Taus(make_config(table=TAU_TABLES[tag]))
+    beta, loge, u = G[tag + "_beta"], G[tag + "_loge"], G[tag + "_u_raw"]
+    np.testing.assert_allclose(t.tau_energy(beta, loge, u, u_raw=True), G[tag + "_tauEnergy"],
+                               rtol=1e-12)
+    np.testing.assert_allclose(t(beta, loge, u=u, u_raw=True)[2], G[tag + "_tauEnergy"],
+                               rtol=1e-12)
+    z = t.tau_energy(beta, loge) / 10**loge  # own draws: never outside the table
+    assert np.isfinite(z).all() and z.min() >= t.tau_cdf_grid["e_tau_frac"][0]
+    if tag == "nls0":
+        with pytest.raises(ValueError):  # a caller's u is used as it is, like the reference's
+            t.tau_energy(beta, loge, u)
+        cfg = make_config(table=TAU_TABLES[tag], loge=11.5, n=20000)
+        sim = nss.compute(cfg, seed=3)  # Philox uniforms, ~1 % of them below cdf[0] = 0.0134
+        assert len(sim) > 19000 and np.isfinite(sim["tauEnergy"]).all()
+        r = nss.run_acceptance(cfg, 20000, seed=3)
+        assert np.isfinite(r[0])
 
 
 def test_altdec_and_spectrum(nss, golden):
@@ -228,7 +289,14 @@ def test_compute_writes_fits(nss, tmp_path):
     cfg = make_config(n=300)
     fn = tmp_path / "run.fits"
     sim = nss.compute(cfg, output_file=str(fn), seed=3)
+    assert not fn.exists()  # like the reference: only write_stages writes inside compute()
+    sim.write(str(fn), format="fits", overwrite=True)  # apps/run.py:209-210
     back = R.read_fits_table(str(fn))
+    assert back.colnames == sim.colnames and len(back) == len(sim)
+    fn2 = tmp_path / "staged.fits"
+    sim2 = nss.compute(cfg, output_file=str(fn2), seed=3, write_stages=True)
+    back = R.read_fits_table(str(fn2))
+    assert np.array_equal(np.asarray(sim2["numPEs"]), np.asarray(sim["numPEs"]))
     assert back.colnames == sim.colnames and len(back) == len(sim)
     assert np.array_equal(back["numPEs"], sim["numPEs"])
     assert back.meta["ONEVPASS"] == sim.meta["ONEVPASS"][0]
@@ -438,6 +506,9 @@ def test_cli_run_writes_results(nss, tmp_path):
     t = R.read_fits_table(out)
     assert len(t.colnames) == 15 and 1900 < len(t) <= 2000
     assert np.all(t["log_e_nu"] == 9.0)
+    out2 = str(tmp_path / "none.fits")  # -n / --no-result-file (apps/run.py:73-78, 209-210)
+    res = r.invoke(cli, ["run", cfg, "500", "--no-result-file", "-o", out2])
+    assert res.exit_code == 0 and not (tmp_path / "none.fits").exists()
     acc = r.invoke(cli, ["run", cfg, "2e3", "--monospectrum", "9", "--monocloud", "3.0",
                          "--seed", "11", "--acceptance-only"])
     assert acc.exit_code == 0, acc.output
@@ -539,13 +610,18 @@ def test_gaisser_hillas_fluctuated_needs_uniforms(nss):
     p = _lib.NssParams()
     p.eas_profile = 2
     x = _lib.to_device(np.ones(4))
+    ws = _lib.eas_workspace(4)
     rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
-                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, None)
+                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, _lib.ptr(ws), None)
     assert rc == -2  # null u_profile
     p.eas_profile, p.has_cloud = 0, 2
     rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
-                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, None)
+                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, _lib.ptr(ws), None)
     assert rc == -2  # per-event cloud model without cloud tops
+    p.has_cloud = 0
+    rc = _lib.lib().nss_cphotang(ctypes.byref(p), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+                                 None, 4, _lib.ptr(x), _lib.ptr(x), None, None, None)
+    assert rc == -2  # no workspace
     with pytest.raises(ValueError):
         nss.CphotAng(525.0, "Linsley")
 
@@ -708,3 +784,41 @@ def test_compute_sharded_over_ranks(nss):
         np.testing.assert_allclose(r[2]["OMCINT"], one.meta["OMCINT"][0], rtol=1e-13)
         np.testing.assert_allclose(r[2]["OMCINTGO"], one.meta["OMCINTGO"][0], rtol=1e-13)
         np.testing.assert_allclose(r[2]["OMCINTUN"], one.meta["OMCINTUN"][0], rtol=1e-10)
+
+
+def test_eas_entry_points_are_reentrant(nss, eas_large):
+    """Two nss_cphotang launches in flight at once on different streams, each with its own
+    caller-supplied workspace, return bit for bit what the same launches return one after the
+    other: the entry points keep no per-call state of their own (include/nss_b200.h)."""
+    import ctypes
+
+    import torch
+
+    from nuspacesim_b200 import _lib
+
+    L = _lib.lib()
+    p = nss.CphotAng(525.0, "Greisen").params
+    sets = []
+    for tag in ("c1", "e10"):
+        ref = eas_large[tag]
+        sets.append([_lib.to_device(ref[k]) for k in ("beta", "alt", "eshow")])
+
+    def launch(x, stream, ws):
+        n = x[0].numel()
+        d, c = _lib.empty(n), _lib.empty(n)
+        rc = L.nss_cphotang(ctypes.byref(p), _lib.ptr(x[0]), _lib.ptr(x[1]), _lib.ptr(x[2]), None,
+                            None, n, _lib.ptr(d), _lib.ptr(c), None, _lib.ptr(ws),
+                            ctypes.c_void_p(stream.cuda_stream))
+        assert rc == 0
+        return d, c
+
+    ws = [_lib.eas_workspace(x[0].numel()) for x in sets]
+    main = torch.cuda.current_stream()
+    serial = [launch(x, main, w) for x, w in zip(sets, ws)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(3):  # interleave the two event sets on two streams, several times over
+        conc = [launch(x, s, w) for x, s, w in zip(sets, streams, ws)]
+        torch.cuda.synchronize()
+        for (d0, c0), (d1, c1) in zip(serial, conc):
+            assert torch.equal(d0, d1) and torch.equal(c0, c1)

@@ -58,7 +58,10 @@ def test_null_and_bad_arguments_are_rejected_without_gpu():
     assert L.nss_alt_dec(None, None, None, None, -1, None, None, None) == -1
     assert L.nss_alt_dec(None, None, None, None, 0, None, None, None) == 0  # empty input
     eas_args = lambda n: (ctypes.byref(p), None, None, None, None, None, None, n, None, None,
-                          None, None, None, None)
+                          None, None, None, None, None)
+    assert L.nss_eas_workspace_bytes(0) == 256  # the work counter alone
+    assert L.nss_eas_workspace_bytes(1024) == 256 + (144 + 48) * 1024  # EasPrep + EasAcc records
+    assert L.nss_acceptance_workspace_bytes(4096) > L.nss_eas_workspace_bytes(4096)
     assert L.nss_eas_optical(*eas_args(0)) == 0
     assert L.nss_eas_optical(*eas_args(3)) == -2
     p.eas_profile = 7  # unknown longitudinal profile
@@ -205,6 +208,52 @@ def test_results_table_fits_roundtrip(tmp_path):
     assert np.array_equal(back["numPEs"], t["numPEs"])
     assert back.meta["OMCINT"] == 0.125
     assert R.output_filename("x.fits") == "x.fits"
+
+
+def test_results_fits_file_is_standard_conforming(tmp_path):
+    """The results file checked by an independent implementation of the FITS 4.0 layout rules
+    (tests/fits_check.py shares no code with the writer): 2880-byte blocks, card character set,
+    upper-case keywords (astropy writes the reference's ``simTime`` as SIMTIME), mandatory
+    keyword order of the primary HDU and the BINTABLE extension, TFORMn, NAXIS1, big-endian
+    'D' columns, fills -- and the decoded table equals what was written, bit for bit."""
+    from fits_check import FitsError, check_results_file
+    from nuspacesim_b200 import results_table as R
+
+    cfg = make_config()
+    t = R.init(cfg)
+    rng = np.random.default_rng(3)
+    names = ["beta_rad", "theta_rad", "path_len", "init_lat", "init_lon", "log_e_nu", "tauBeta",
+             "tauLorentz", "tauEnergy", "showerEnergy", "tauExitProb", "altDec", "lenDec",
+             "numPEs", "costhetaChEff"]
+    cols = [rng.standard_normal(361) * 10.0 ** rng.integers(-12, 12) for _ in names]
+    cols[3][5] = np.nan
+    t.add_columns(cols, names)
+    t.meta["OMCINT"] = (0.1291, "Optical MonteCarlo Integral")
+    t.meta["ONEVPASS"] = (1206, "Optical Number of Passing Events")
+    t.meta["OMCINTUN"] = (float("nan"), "Stat unc of MonteCarlo Integral")
+    t.meta["HIERARCH Config note"] = "it's a 'quoted' value " + "x" * 90  # cut, quotes kept legal
+    fn = str(tmp_path / "r.fits")
+    t.write(fn, format="fits")
+    meta, table = check_results_file(fn)
+    assert list(table) == names and "SIMTIME" in meta and "simTime" not in meta
+    for n, c in zip(names, cols):
+        assert np.array_equal(np.array(table[n]), c, equal_nan=True), n
+    assert meta["OMCINT"] == 0.1291 and meta["ONEVPASS"] == 1206
+    assert meta["HIERARCH Config detector initial_position altitude"] == "525.0 km"
+    assert meta["HIERARCH Config note"].startswith("it's a 'quoted' value xxx")
+    # the empty table (no valid events) is a legal file too
+    e = R.init(cfg)
+    fe = str(tmp_path / "e.fits")
+    e.write(fe, format="fits")
+    check_results_file(fe)
+    # and the checker does reject what the previous writer produced: a lower-case keyword
+    raw = bytearray(open(fn, "rb").read())
+    i = raw.find(b"SIMTIME ")
+    raw[i:i + 8] = b"simTime "
+    bad = str(tmp_path / "bad.fits")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(FitsError):
+        check_results_file(bad)
 
 
 def test_shard_range_partitions_exactly():

@@ -296,3 +296,27 @@ def test_oracle_against_live_reference():
     d, c, _ = O.cphotang(b, a, e)
     assert rel_err(d, want[:, 0]).max() < 1e-3
     assert rel_err(c, want[:, 1]).max() < 2e-6
+
+
+@pytest.mark.parametrize("tag", ["nls0", "np3"])
+def test_tau_energy_raw_uniforms_vs_reference(tag):
+    """Taus.tau_energy WITHOUT u, as compute() calls it: the reference draws
+    np.random.uniform(cdfs[:, 0], 1.0) (utils/cdf.py:419-423).  The fixture
+    (tests/golden/make_golden_taus_raw.py) holds the legacy generator's raw outputs and the
+    reference's results; the nuleptonsim CDF starts at up to 0.0134, so using the raw draws as
+    they are would leave the table."""
+    import os
+
+    from conftest import GOLDEN
+
+    G = np.load(os.path.join(GOLDEN, "taus_raw.npz"))
+    T = load_tables(*TAU_TABLES[tag])
+    args = (T["cdf"], T["cdf_log_e_nu"], T["cdf_beta_rad"], T["cdf_e_tau_frac"],
+            G[tag + "_beta"], G[tag + "_loge"], G[tag + "_u_raw"])
+    te = O.tau_energy(*args, u_raw=True)
+    np.testing.assert_allclose(te, G[tag + "_tauEnergy"], rtol=1e-13)
+    if tag == "nls0":
+        with pytest.raises(ValueError):
+            O.tau_energy(*args)
+    else:  # first CDF column identically 0: the mapping is the identity
+        assert np.array_equal(O.tau_energy(*args), te)
