@@ -45,6 +45,9 @@ struct Ops32 {
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
     return v;
   }
+  static __device__ __forceinline__ float max_f(float v) {  // v >= 0: bit pattern is monotone
+    return __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));
+  }
   static __device__ __forceinline__ int sum_i(int v) { return __reduce_add_sync(FULL, v); }
   static __device__ __forceinline__ int max_i(int v) { return __reduce_max_sync(FULL, v); }
   static __device__ __forceinline__ int min_i(int v) { return __reduce_min_sync(FULL, v); }

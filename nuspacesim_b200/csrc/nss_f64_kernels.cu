@@ -397,6 +397,39 @@ inline TabView view_of(const NssTables* t) {
   return v;
 }
 
+// Tau exit-probability table (log10 P over log_e_nu x beta, 25 x 51 float64 = 10.2 KB, plus its
+// two axes) staged in shared memory by the block: the bracket searches and the four gathers of
+// tau_exit_prob_event then hit shared memory instead of L2.  The kernels that use it run a
+// grid of a few blocks per SM (tau_grid) so that one staging pass serves ~2000 events.  The
+// CDF grid (25 x 51 x 71 float64 = 724 KB) does not fit the 227 KB of an SM and stays
+// L2-resident.  smem_doubles == 0 (a table too large to stage): global pointers are kept.
+__device__ inline TabView stage_pexit(const TabView& t, double* sm, int smem_doubles) {
+  const int np = t.nE * t.nB;
+  if (smem_doubles < np + t.nE + t.nB) return t;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) sm[i] = t.pexit_log10[i];
+  for (int i = threadIdx.x; i < t.nE; i += blockDim.x) sm[np + i] = t.pexit_loge[i];
+  for (int i = threadIdx.x; i < t.nB; i += blockDim.x) sm[np + t.nE + i] = t.pexit_beta[i];
+  __syncthreads();
+  TabView s = t;
+  s.pexit_log10 = sm;
+  s.pexit_loge = sm + np;
+  s.pexit_beta = sm + np + t.nE;
+  return s;
+}
+
+// shared-memory doubles to ask for (0 if the table exceeds the default 48 KB dynamic limit)
+inline int pexit_smem_doubles(const TabView& t) {
+  const int64_t d = (int64_t)t.nE * t.nB + t.nE + t.nB;
+  return d * 8 <= 48 * 1024 ? (int)d : 0;
+}
+
+// grid of the table kernels: at most 8 blocks of 256 threads per SM
+inline int tau_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = 148LL * 8;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
 // cell index and weight like scipy's RegularGridInterpolator._find_indices:
 // i = searchsorted(axis, x) - 1 clipped to [0, n-2]; w = (x - axis[i]) / (axis[i+1] - axis[i])
 __device__ inline void bracket(const double* __restrict__ ax, int n, double x, int& i, double& w) {
@@ -498,9 +531,11 @@ __device__ inline void alt_dec_event(double R, double beta, double tauBeta, doub
 }
 
 __global__ void __launch_bounds__(256)
-tau_kernel(NssParams p, TabView t, const double* __restrict__ beta, const double* __restrict__ le,
-           const double* __restrict__ u, int64_t n, double* tb, double* tl, double* te, double* sh,
-           double* pex, int32_t* flags, int what, bool raw) {
+tau_kernel(NssParams p, TabView tg, int smem_doubles, const double* __restrict__ beta,
+           const double* __restrict__ le, const double* __restrict__ u, int64_t n, double* tb,
+           double* tl, double* te, double* sh, double* pex, int32_t* flags, int what, bool raw) {
+  extern __shared__ double tau_sm[];
+  const TabView t = (what == 2) ? tg : stage_pexit(tg, tau_sm, smem_doubles);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     if (what == 1) {
@@ -640,8 +675,10 @@ struct FrontBufs {
 
 // throw -> spectrum -> taus -> altDec for thrown events [first, first+n) from Philox.
 __global__ void __launch_bounds__(256)
-front_kernel(NssParams p, TabView t, CloudMapView cm, uint64_t seed, uint64_t first, int64_t n,
-             FrontBufs b, int32_t* flags) {
+front_kernel(NssParams p, TabView tg, int smem_doubles, CloudMapView cm, uint64_t seed,
+             uint64_t first, int64_t n, FrontBufs b, int32_t* flags) {
+  extern __shared__ double front_sm[];
+  const TabView t = stage_pexit(tg, front_sm, smem_doubles);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t w0[4], w1[4];
@@ -918,9 +955,10 @@ static int tau_launch(const NssParams* p, const NssTables* t, const double* b, c
   NssParams pp;
   memset(&pp, 0, sizeof(pp));
   if (p) pp = *p;
-  tau_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pp, view_of(t), b, le, u, n, tb,
-                                                                 tl, te, sh, pex, flags, what,
-                                                                 u_raw != 0);
+  const TabView tv = view_of(t);
+  const int smd = pexit_smem_doubles(tv);
+  tau_kernel<<<tau_grid(n), 256, (size_t)smd * 8, (cudaStream_t)stream>>>(
+      pp, tv, smd, b, le, u, n, tb, tl, te, sh, pex, flags, what, u_raw != 0);
   return (int)cudaGetLastError();
 }
 
@@ -1061,10 +1099,11 @@ extern "C" int nss_run_acceptance(const NssParams* p, const NssTables* t, uint64
   double sn, sw;
   spec_norms(p, sn, sw);
   TabView tv = view_of(t);
+  const int smd = pexit_smem_doubles(tv);
   for (int64_t off = 0; off < n; off += batch) {
     const int64_t m = (n - off) < batch ? (n - off) : batch;
-    front_kernel<<<grid_for(m, 256), 256, 0, s>>>(*p, tv, g_cloud, seed,
-                                                  first_event + (uint64_t)off, m, b, flags);
+    front_kernel<<<tau_grid(m), 256, (size_t)smd * 8, s>>>(
+        *p, tv, smd, g_cloud, seed, first_event + (uint64_t)off, m, b, flags);
     int rc = nss_eas_optical(p, b.beta, b.alt, b.shower, b.mask,
                              p->eas_profile == 2 ? b.uprof : nullptr,
                              p->has_cloud == 2 ? b.cloud : nullptr, m, b.npe, b.cth, nullptr,

@@ -14,6 +14,7 @@ struct Ops1 {
   static float scan_f(float v) { return v; }
   static double sum_d(double v) { return v; }
   static float sum_f(float v) { return v; }
+  static float max_f(float v) { return v; }
   static int sum_i(int v) { return v; }
   static int max_i(int v) { return v; }
   static int min_i(int v) { return v; }

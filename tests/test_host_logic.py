@@ -310,6 +310,86 @@ def emul():
     return run
 
 
+@pytest.fixture(scope="module")
+def emul32():
+    """The walk as a 32-lane warp on the host (tests/host_emul/eas_host_emul32.cpp: one fiber
+    per lane, every warp collective a rendezvous).  Returns run(...) -> (d, c, stats8)."""
+    src = os.path.join(ROOT, "tests", "host_emul", "eas_host_emul32.cpp")
+    lib = os.path.join(ROOT, "tests", "host_emul", "libeas_host_emul32.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
+                           os.path.join(ROOT, "nuspacesim_b200", "csrc"), src, "-o", lib])
+    L = ctypes.CDLL(lib)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+    def run(beta, alt, es, det=525.0, top=None, profile=0, rows=None, cloud_ev=None):
+        beta, alt, es = (np.ascontiguousarray(x, float) for x in (beta, alt, es))
+        n = beta.size
+        npe, cc, d, c = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+        st = (ctypes.c_ulonglong * 8)()
+        rows = None if rows is None else np.ascontiguousarray(rows, float)
+        cloud_ev = None if cloud_ev is None else np.ascontiguousarray(cloud_ev, float)
+        diverged = L.nss_emul32_eas_profile(
+            ctypes.c_longlong(n), dp(beta), dp(alt), dp(es), ctypes.c_double(det),
+            ctypes.c_double(2.5), ctypes.c_double(0.2), ctypes.c_double(10.0),
+            ctypes.c_int(top is not None), ctypes.c_float(top or 0.0), dp(npe), dp(cc), dp(d),
+            dp(c), st, ctypes.c_int(profile), None if rows is None else dp(rows),
+            None if cloud_ev is None else dp(cloud_ev))
+        assert diverged == 0, "lanes did not all arrive at the same warp collective"
+        return d, c, list(st)
+
+    return run
+
+
+def test_warp_logic_on_host_cloud_sweep(emul32, golden):
+    """The 32-lane walk (chunk votes, scan carry, tail skip with per-lane histories) on the
+    reference's cloud sweep: a cloud deck makes the LAST steps of a shower its whole signal,
+    which is where a tail skip that trusts a lane without history goes wrong (seen on the GPU:
+    66 % on one event at a 6 km cloud top before the bound became warp-wide)."""
+    sw = golden["eas"]["sweep"]
+    for det in (525.0, 33.0):
+        for top in (-np.inf, 2.0, 6.0, 12.0):
+            m = (sw[:, 0] == det) & (sw[:, 4] == top)
+            if not m.any():
+                continue
+            d, c, st = emul32(sw[m, 1], sw[m, 2], sw[m, 3], det, None if top == -np.inf else top)
+            assert np.array_equal(d == 0, sw[m, 5] == 0), (det, top)
+            rr = rel_err(d, sw[m, 5])
+            assert rr.max() < 5e-3 and np.median(rr) < 1e-4, (det, top, rr.max())
+            assert rel_err(c, sw[m, 6]).max() < 3e-5
+
+
+@pytest.mark.parametrize("tag", ["c1", "e10"])
+def test_warp_logic_on_host_vs_single_lane(emul, emul32, eas_large, tag):
+    """32 lanes per event against one lane per event on a sample of the reference events: the
+    same arithmetic, so only the chunk-level decisions (which chunks count as tail) and the
+    float32 order of the warp scan differ -- and the tail skip must really skip."""
+    ref = eas_large[tag]
+    sl = slice(0, 96)
+    b, a, e = ref["beta"][sl], ref["alt"][sl], ref["eshow"][sl]
+    d32, c32, st = emul32(b, a, e)
+    _, _, d1, c1, _ = emul(b, a, e)
+    r = rel_err(d32, d1)
+    # (max: showers with a flat RN maximum -- the float32 order of the prefix sum decides which
+    # step is argmax RN, one step = 1.8e-4 in Cherenkov area; the reference has the same noise)
+    assert np.median(r) < 2e-6 and np.percentile(r, 95) < 2e-5 and r.max() < 2.5e-3, \
+        (np.median(r), r.max())
+    assert rel_err(c32, c1).max() < 2e-5
+    rr = rel_err(d32, ref["dphots"][sl])
+    assert np.median(rr) < 5e-5 and rr.max() < 2.5e-3
+    n_val, n_tail = st[2], st[7]
+    assert 0.005 * n_val < n_tail < 0.25 * n_val, (n_val, n_tail)  # whole chunks of 32 steps
+
+
+def test_warp_logic_on_host_gaisser_hillas(emul32, eas_gh):
+    ref = eas_gh["c1", "ghf"]
+    sl = slice(0, 48)
+    d, c, _ = emul32(ref["beta"][sl], ref["alt"][sl], ref["eshow"][sl], 525.0, None, 2,
+                     ref["rows"][sl])
+    rr = rel_err(d, ref["dphots"][sl])
+    assert np.median(rr) < 7e-5 and rr.max() < 2.5e-3
+    assert rel_err(c, ref["cang"][sl]).max() < 5e-5
+
+
 def test_kernel_arithmetic_on_host_vs_oracle(emul, golden):
     """nss_eas_core.cuh compiled for the host (W = 1) vs the oracle and the reference."""
     sw = golden["eas"]["sweep"]
