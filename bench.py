@@ -429,11 +429,12 @@ def main():
             unit="TFLOP/s", frac=ach / fp32_peak.value if fp32_peak.value else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE eas_walk_kernel launch, read from
             # the newest committed ncu --set full summary under profiles/ (scaled to this run's
-            # events per launch).  The records the kernel must move are 144 B (EasPrep) + 48 B
-            # (EasAcc) per event: the kernel is compute bound (bound = "fp32").
+            # events per launch).  The walk must read 96 B of each event's EasPrep record (the
+            # Gaisser-Hillas third is not touched by the Greisen instantiation) and write the
+            # 48 B EasAcc record: 144 B per event; the kernel is compute bound (bound = "fp32").
             traffic=traffic, traffic_source=traffic_src,
             traffic_unit="bytes per launch (ncu, cold cache)",
-            algorithmic_bytes=192.0 * ev_per_launch,
+            algorithmic_bytes=144.0 * ev_per_launch,
             peak_source="nss_microbench_peaks on this device (FFMA chains; MEASURED_PEAKS.json "
                         "has no FP32 entry), of measured",
             sfu=dict(achieved=transc_step / eas_s_per_step * 1e-12, peak=mufu_peak.value,

@@ -244,54 +244,15 @@ def _gather_rank_sums(row):
 
 
 def _host_columns(names, n):
-    """Full-length host arrays the slices' columns are copied into.
-
-    Page-locked when torch's caching host allocator already holds enough free page-locked
-    memory (a process that calls compute() repeatedly) or when there is no way to ask;
-    otherwise -- the first call of a process, i.e. the reference's `nuspacesim run` usage --
-    plain pageable memory: page-locking 1.2 GB takes ~1.6 s, copying into pageable memory
-    ~0.3 s.  In that case the pool is warmed in the background for the next call."""
+    """Full-length host arrays the slices' columns are copied into: page-locked (torch's
+    caching host allocator recycles them between calls) unless they exceed PINNED_MAX_BYTES,
+    in which case plain pageable memory is used (slower copies, but page-locked memory is a
+    scarce resource: 120 B per thrown event)."""
     torch = _lib.torch_cuda()
-    need = len(names) * n * 8
-    pinned = need <= PINNED_MAX_BYTES
-    if pinned and os.environ.get("NSS_HOST_COLUMNS", "auto") == "auto":
-        try:
-            st = torch.cuda.host_memory_stats()
-            free = st.get("reserved_bytes.current", 0) - st.get("allocated_bytes.current", 0)
-            pinned = free >= need
-        except Exception:
-            pinned = True
-        if not pinned:
-            _warm_pinned_pool(len(names), n)
-    elif os.environ.get("NSS_HOST_COLUMNS") == "pageable":
+    pinned = len(names) * n * 8 <= PINNED_MAX_BYTES
+    if os.environ.get("NSS_HOST_COLUMNS") == "pageable":
         pinned = False
     return {nm: torch.empty(n, dtype=torch.float64, pin_memory=pinned) for nm in names}
-
-
-_WARM_THREAD = None
-
-
-def _warm_pinned_pool(ncols, n):
-    """Allocate and release page-locked blocks of the result-column size on a helper thread so
-    that the NEXT compute() call finds them in torch's caching host allocator."""
-    global _WARM_THREAD
-    import threading
-
-    if _WARM_THREAD is not None and _WARM_THREAD.is_alive():
-        return
-    torch = _lib.torch_cuda()
-    dev = torch.cuda.current_device()
-
-    def work():
-        try:
-            torch.cuda.set_device(dev)
-            blocks = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(ncols)]
-            del blocks
-        except Exception:
-            pass
-
-    _WARM_THREAD = threading.Thread(target=work, name="nss-pinned-warm", daemon=True)
-    _WARM_THREAD.start()
 
 
 def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown, step,

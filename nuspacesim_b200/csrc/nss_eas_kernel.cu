@@ -107,7 +107,7 @@ constexpr int walk_block(bool gh) { return gh ? 128 : 32; }
 // instantiation, 48 bytes of spill and 2-4 % slower for the Gaisser-Hillas one, which
 // therefore stays at 5 blocks of 4 warps and 96 registers.
 template <bool GH>
-__global__ void __launch_bounds__(walk_block(GH), GH ? 5 : 22)
+__global__ void __launch_bounds__(walk_block(GH), GH ? 5 : 20)
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
                 unsigned long long* __restrict__ stats) {
