@@ -303,21 +303,34 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     sums, off = [], 0
     thr = config.detector.optical.photo_electron_threshold
     mc_spec_norm = spec_weights_sum = 1.0
-    for k, (lo, hi) in enumerate(bounds):
+    def start_throw(k):
+        """Enqueue slice k's throw + mask scan; its valid-event count travels to pinned host
+        memory right behind them, so reading it later never waits for kernels enqueued after
+        this point (the previous slice's EAS in particular)."""
+        lo, hi = bounds[k]
         d = pre.pop(k)
         if k + PREFETCH_SLICES < len(bounds):
             pre[k + PREFETCH_SLICES] = upload(k + PREFETCH_SLICES)
-        geom = RegionGeom(config, seed=seed)
-        geom.first_event = lo
+        g = RegionGeom(config, seed=seed)
+        g.first_event = lo
         thrown = hi - lo
         if "u4" in d:
             thrown, ev = d["u4"]
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
-        beta_tr, theta, path_len = geom(thrown, device=True)
-        nv = int(beta_tr.numel())
+        g.throw(thrown, defer_count=True)
+        return g, d
+
+    nxt = start_throw(0) if bounds else None
+    for k, (lo, hi) in enumerate(bounds):
+        geom, d = nxt
+        nxt = None
+        nv = geom._n_valid  # waits for THIS slice's throw + scan only
         if nv == 0:
+            if k + 1 < len(bounds):
+                nxt = start_throw(k + 1)
             continue
+        beta_tr, theta, path_len = geom.beta_rad(True), geom.thetas(True), geom.pathLens(True)
 
         def valid_u(name):
             if name in d:
@@ -341,6 +354,10 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
         for n in front:  # these travel while the EAS kernel runs
             sink.copy_into(host[n][off:off + nv], cols[n])
         u_prof = valid_u("u_profile") if eas.params.eas_profile == 2 else None
+        # the next slice's throw goes in front of this slice's EAS kernels: its valid-event
+        # count is on the host long before they finish, and the host never idles the GPU
+        if k + 1 < len(bounds):
+            nxt = start_throw(k + 1)
         cols["numPEs"], cols["costhetaChEff"] = eas(
             beta_tr, cols["altDec"], cols["showerEnergy"], cols["init_lat"], cols["init_lon"],
             cloudf=cloud, u_profile=u_prof)

@@ -48,12 +48,17 @@ class RegionGeom:
         self._n = 0
         self._valid_cache = {}
         self._pos = None
-        self._n_valid = 0
+        self._nv, self._nv_pending = 0, None
 
     # ------------------------------------------------------------------ throw
 
-    def throw(self, u=None):
-        """Throw N events with 4 * u random numbers (region_geometry.py:94-239)."""
+    def throw(self, u=None, defer_count: bool = False):
+        """Throw N events with 4 * u random numbers (region_geometry.py:94-239).
+
+        ``defer_count`` (extension, used by compute()'s pipelined path): do not wait for the
+        number of valid events; it is copied to pinned host memory behind the scan and read --
+        waiting for THAT copy only -- when first needed, so kernels enqueued after this call do
+        not delay it."""
         L = _lib.lib()
         if u is None:
             raise RuntimeError(
@@ -80,7 +85,7 @@ class RegionGeom:
                                    _lib.stream_ptr()),
                 "nss_geom_throw_u",
             )
-        self._scan()
+        self._scan(defer_count)
 
     def _alloc(self, n, soa):
         self._n = n
@@ -91,7 +96,16 @@ class RegionGeom:
         soa.event_mask = self._dev["event_mask"].data_ptr()
         self._valid_cache = {}
 
-    def _scan(self):
+    @property
+    def _n_valid(self):
+        if self._nv is None:
+            pinned, ev = self._nv_pending
+            ev.synchronize()
+            self._nv = int(pinned.item())
+            self._nv_pending = None
+        return self._nv
+
+    def _scan(self, defer_count=False):
         L = _lib.lib()
         n = self._n
         self._pos = _lib.empty(max(n, 1), "int64")
@@ -102,7 +116,15 @@ class RegionGeom:
                             _lib.ptr(nset), _lib.ptr(ws), _lib.stream_ptr()),
             "nss_mask_scan",
         )
-        self._n_valid = int(nset.item())
+        if defer_count and n > 0:
+            torch = _lib.torch_cuda()
+            pinned = torch.empty(1, dtype=torch.int64, pin_memory=True)
+            pinned.copy_(nset, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._nv, self._nv_pending = None, (pinned, ev)
+        else:
+            self._nv = int(nset.item())
 
     def compact(self, full, device: bool = True):
         """Entries of a length-N (thrown-order) array that belong to valid events, in thrown

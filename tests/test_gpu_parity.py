@@ -291,6 +291,8 @@ def test_compute_writes_fits(nss, tmp_path):
     sim = nss.compute(cfg, output_file=str(fn), seed=3)
     assert not fn.exists()  # like the reference: only write_stages writes inside compute()
     sim.write(str(fn), format="fits", overwrite=True)  # apps/run.py:209-210
+    assert not fn.exists()  # compute() leaves the final write to its caller (apps/run.py:209-210)
+    many.write(str(fn), format="fits", overwrite=True)
     back = R.read_fits_table(str(fn))
     assert back.colnames == sim.colnames and len(back) == len(sim)
     fn2 = tmp_path / "staged.fits"
