@@ -500,6 +500,28 @@ def main():
                    # up from the device-resident leg; no page-locked host memory cached yet):
                    # what a one-shot `nuspacesim run` pays on top of start-up
                    cold_call_s=step_s[0], cold_value=n / step_s[0])
+        # the same call with in-kernel Philox instead of host uniforms (`compute(config, seed=s)`,
+        # what `nuspacesim run` does): no host -> device bytes, the same table back
+        cfg_seed = nss.NssConfig()
+        cfg_seed.simulation.thrown_events = n
+        sync_all()
+        ts = []
+        for i in range(1 + k_e2e):
+            if i == 1:
+                sync_all()
+                t0 = time.perf_counter()
+            t1 = time.perf_counter()
+            sim = nss.compute(cfg_seed, seed=SEED + 7 * rank + i)
+            ts.append(time.perf_counter() - t1)
+        torch.cuda.synchronize()
+        dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+        e2e["seed_variant"] = dict(
+            value=n * world * k_e2e / float(dts.item()), unit=UNIT, h2d_bytes_per_step=0,
+            d2h_bytes_per_step=int(d2h), steps=k_e2e, rank0_call_s=ts,
+            api="nuspacesim_b200.compute(config, seed=s) -> 15-column table on the host")
+        del sim
 
     if rank == 0:
         line = dict(

@@ -194,6 +194,15 @@ def to_device(x, dtype="float64"):
 
 
 _H2D_STREAM = None
+_SIDE_STREAM = None
+
+
+def side_stream():
+    """A stream for small read-backs that must not sit in front of the caller's kernels."""
+    global _SIDE_STREAM
+    if _SIDE_STREAM is None:
+        _SIDE_STREAM = torch_cuda().cuda.Stream()
+    return _SIDE_STREAM
 
 
 def to_device_prefetch(x, dtype="float64"):

@@ -35,6 +35,8 @@ __all__ = ["compute", "run_acceptance"]
 SLICE_EVENTS = 1 << 21
 #: slices whose uniforms are uploaded ahead of the one being computed
 PREFETCH_SLICES = 2
+#: enqueue the next slice's throw ahead of the current slice's EAS kernels
+PIPELINE_THROW = os.environ.get("NSS_PIPELINE_THROW", "1") != "0"
 #: result columns larger than this in total are not page-locked (pinning is ~1 GB/s and
 #: page-locked memory is a scarce resource: 120 B per thrown event)
 PINNED_MAX_BYTES = int(os.environ.get("NSS_PINNED_MAX_BYTES", 16 << 30))
@@ -243,16 +245,49 @@ def _gather_rank_sums(row):
     return np.stack([o.cpu().numpy() for o in out])
 
 
-def _host_columns(names, n):
-    """Full-length host arrays the slices' columns are copied into: page-locked (torch's
-    caching host allocator recycles them between calls) unless they exceed PINNED_MAX_BYTES,
-    in which case plain pageable memory is used (slower copies, but page-locked memory is a
-    scarce resource: 120 B per thrown event)."""
-    torch = _lib.torch_cuda()
-    pinned = len(names) * n * 8 <= PINNED_MAX_BYTES
-    if os.environ.get("NSS_HOST_COLUMNS") == "pageable":
-        pinned = False
-    return {nm: torch.empty(n, dtype=torch.float64, pin_memory=pinned) for nm in names}
+class _HostColumns:
+    """The full-length host arrays the slices' columns are copied into (utils/host_pool.py:
+    page-locked on a helper thread, recycled between calls).  Until the block is ready the
+    copies are only queued -- the device tensors stay alive -- so that a cold first call
+    computes while its result memory is being page-locked instead of waiting for it."""
+
+    def __init__(self, names, n, sink):
+        from .utils import host_pool
+
+        torch = _lib.torch_cuda()
+        self.sink, self.queue = sink, []
+        self.pend = None
+        mode = os.environ.get("NSS_HOST_COLUMNS", "pool")
+        if len(names) * n * 8 > PINNED_MAX_BYTES or mode == "pageable":
+            # too large to page-lock (or asked not to): plain pageable memory
+            self.cols = {nm: torch.empty(n, dtype=torch.float64) for nm in names}
+        elif mode == "torch":  # torch's caching host allocator (cudaHostAlloc)
+            self.cols = {nm: torch.empty(n, dtype=torch.float64, pin_memory=True) for nm in names}
+        else:
+            self.pend = host_pool.PendingColumns(names, n)
+
+    def _ready(self):
+        if self.pend is not None and self.pend.ready():
+            self.cols = self.pend.wait()
+            self.pend = None
+        return self.pend is None
+
+    def put(self, name, off, nv, t):
+        self.queue.append((name, off, nv, t))
+        if self._ready():
+            self.flush()
+
+    def flush(self):
+        for name, off, nv, t in self.queue:
+            self.sink.copy_into(self.cols[name][off:off + nv], t)
+        self.queue = []
+
+    def finish(self):
+        if self.pend is not None:
+            self.cols = self.pend.wait()
+            self.pend = None
+        self.flush()
+        return self.cols
 
 
 def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown, step,
@@ -298,7 +333,7 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     pre = {k: upload(k) for k in range(min(PREFETCH_SLICES, len(bounds)))}
 
     names = [n for g in COLUMN_GROUPS for n in g]
-    host = _host_columns(names, max(last - first, 1))
+    host = _HostColumns(names, max(last - first, 1), sink)
     WHICH = {"u_spec": 0, "u_tau": 1, "u_dec": 2, "u_profile": 3}
     sums, off = [], 0
     thr = config.detector.optical.photo_electron_threshold
@@ -352,30 +387,34 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
                                                     valid_u("u_dec"))
         front = [n for n in names if n not in ("numPEs", "costhetaChEff")]
         for n in front:  # these travel while the EAS kernel runs
-            sink.copy_into(host[n][off:off + nv], cols[n])
+            host.put(n, off, nv, cols[n])
         u_prof = valid_u("u_profile") if eas.params.eas_profile == 2 else None
         # the next slice's throw goes in front of this slice's EAS kernels: its valid-event
         # count is on the host long before they finish, and the host never idles the GPU
-        if k + 1 < len(bounds):
+        if k + 1 < len(bounds) and PIPELINE_THROW:
             nxt = start_throw(k + 1)
         cols["numPEs"], cols["costhetaChEff"] = eas(
             beta_tr, cols["altDec"], cols["showerEnergy"], cols["init_lat"], cols["init_lon"],
             cloudf=cloud, u_profile=u_prof)
         for n in ("numPEs", "costhetaChEff"):
-            sink.copy_into(host[n][off:off + nv], cols[n])
+            host.put(n, off, nv, cols[n])
         sums.append(geom.mcintegral(cols["numPEs"], cols["costhetaChEff"], cols["tauExitProb"],
                                     thr, mc_spec_norm, spec_weights_sum, device_sums=True))
         off += nv
+        if nxt is None and k + 1 < len(bounds):
+            nxt = start_throw(k + 1)
 
     logv(f"\tThrew {last - first} neutrinos. {off} were valid.")
     if off == 0 and not shard:
         print("\tWARNING: No valid events thrown! Exiting early! Check geometry!")
+        host.finish()
         return sim
     # (slices, 8) on the device: sum geo, sum f, M2, n_pass, n_valid, ... -> one host read
     S = torch.stack(sums).cpu().numpy()[:, :5] if sums else np.zeros((0, 5))
+    hcols = host.finish()
     sink.synchronize()
     for group in COLUMN_GROUPS:
-        sim.add_columns([host[n].numpy()[:off] for n in group], names=group)
+        sim.add_columns([hcols[n].numpy()[:off] for n in group], names=group)
     mine = _merge_sums(S)
     tot = _merge_sums(_gather_rank_sums(mine)) if shard else mine
     mcnorm = float(RegionGeom(config, seed=seed).mcnorm)

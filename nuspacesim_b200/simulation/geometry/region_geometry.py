@@ -117,11 +117,20 @@ class RegionGeom:
             "nss_mask_scan",
         )
         if defer_count and n > 0:
+            # on a side stream: behind the scan, but not in front of whatever the caller
+            # enqueues next on its own stream (an 8-byte copy queues behind megabytes of
+            # column copies in the copy engine; the compute stream must not wait for that)
             torch = _lib.torch_cuda()
             pinned = torch.empty(1, dtype=torch.int64, pin_memory=True)
-            pinned.copy_(nset, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
+            done = torch.cuda.Event()
+            done.record()
+            side = _lib.side_stream()
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                pinned.copy_(nset, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            nset.record_stream(side)
             self._nv, self._nv_pending = None, (pinned, ev)
         else:
             self._nv = int(nset.item())

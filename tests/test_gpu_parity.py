@@ -291,8 +291,6 @@ def test_compute_writes_fits(nss, tmp_path):
     sim = nss.compute(cfg, output_file=str(fn), seed=3)
     assert not fn.exists()  # like the reference: only write_stages writes inside compute()
     sim.write(str(fn), format="fits", overwrite=True)  # apps/run.py:209-210
-    assert not fn.exists()  # compute() leaves the final write to its caller (apps/run.py:209-210)
-    many.write(str(fn), format="fits", overwrite=True)
     back = R.read_fits_table(str(fn))
     assert back.colnames == sim.colnames and len(back) == len(sim)
     fn2 = tmp_path / "staged.fits"
@@ -723,6 +721,8 @@ def test_compute_sliced_pipeline_equals_unsliced(nss, mode, tmp_path):
     np.testing.assert_allclose(many.meta["OMCINTUN"][0], one.meta["OMCINTUN"][0], rtol=1e-10)
     from nuspacesim_b200 import results_table as R
 
+    assert not fn.exists()  # compute() leaves the final write to its caller (apps/run.py:209-210)
+    many.write(str(fn), format="fits", overwrite=True)
     back = R.read_fits_table(str(fn))
     assert np.array_equal(back["numPEs"], one["numPEs"])
 

@@ -609,3 +609,57 @@ def test_kernel_arithmetic_on_host_vs_large_reference_sample(emul, eas_large, ta
     check_engine_vs_reference(d, c, ref, f"host-emul/{tag}")
     ro = rel_err(d, ref["oracle_dphots"])
     assert np.median(ro) < 5e-6  # and an order of magnitude closer to the oracle
+
+
+def test_host_column_pool_recycles_blocks(monkeypatch):
+    """utils/host_pool.py (result columns of compute()): one mapping per table, faulted in and
+    registered on a helper thread, handed back to the pool when the LAST NumPy view of the
+    table dies, and reused by the next table of the same size (cudart mocked: no GPU here)."""
+    import gc
+    import types
+
+    import torch
+
+    from nuspacesim_b200 import _lib
+    from nuspacesim_b200.utils import host_pool as H
+
+    calls = []
+
+    class RT:
+        def cudaHostRegister(self, addr, nbytes, flags):
+            calls.append(("reg", addr, nbytes))
+            return 0
+
+        def cudaHostUnregister(self, addr):
+            calls.append(("unreg", addr))
+            return 0
+
+    cuda = types.SimpleNamespace(cudart=lambda: RT(), current_device=lambda: 0,
+                                 set_device=lambda d: None)
+    monkeypatch.setattr(_lib, "torch_cuda",
+                        lambda: types.SimpleNamespace(cuda=cuda, from_numpy=torch.from_numpy))
+    monkeypatch.setattr(H, "_free", [])
+    monkeypatch.setattr(H, "_live", {})
+    n = 300_000
+    p = H.PendingColumns(["a", "b", "c"], n)
+    cols = p.wait()
+    assert p.pinned and p.ready() and [c.numel() for c in cols.values()] == [n] * 3
+    assert calls == [("reg", calls[0][1], 3 * n * 8)]
+    cols["b"].numpy()[:] = 7.0
+    keep = cols["b"].numpy()[5:9]        # what a results table would hold on to
+    del cols, p
+    gc.collect()
+    assert len(H._live) == 1 and not H._free and keep.sum() == 28.0
+    del keep
+    gc.collect()
+    assert not H._live and len(H._free) == 1
+    q = H.PendingColumns(["a", "b", "c"], n)   # same size: no thread, no new registration
+    assert q._thread is None and len(calls) == 1 and not H._free
+    r = H.PendingColumns(["a"], 10)            # different size: a new block
+    r.wait()
+    assert len(calls) == 2
+    del q, r
+    gc.collect()
+    assert len(H._free) == 2
+    H._cleanup()
+    assert [c[0] for c in calls].count("unreg") == 2 and not H._free
