@@ -127,7 +127,7 @@ EAS_LARGE_TAGS = ("c1", "e7", "e9", "e10", "pl10")
 def eas_large():
     """~31 000 events of the reference's CphotAng.run (tests/golden/make_golden_eas_large.py)
     and, per event, the oracle's own response to perturbations of the size of the reference's
-    float32 noise (O.conditioning; DESIGN.md 5.1)."""
+    float32 noise (O.conditioning; DESIGN.md 5.4)."""
     from oracle import nss_oracle as O
 
     G = np.load(os.path.join(GOLDEN, "eas_large.npz"))
