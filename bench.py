@@ -364,6 +364,11 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
+    numa = None
+    if world > 1 and os.environ.get("NSS_BENCH_NUMA", "1") != "0":
+        from nuspacesim_b200.utils.affinity import bind_to_device_node
+
+        numa = bind_to_device_node(local)  # host buffers of this rank stay next to its GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -511,7 +516,7 @@ def main():
                    api="nuspacesim_b200.compute(config, uniforms=<pinned host arrays>) -> "
                        "15-column table + OMCINT meta on the host",
                    mcint=float(sim.meta["OMCINT"][0]), n_valid=len(sim),
-                   per_rank_s=per_rank, rank0_call_s=step_s,
+                   per_rank_s=per_rank, rank0_call_s=step_s, rank0_numa_binding=numa,
                    # first compute() call of this process (library and CUDA context already
                    # up from the device-resident leg; no page-locked host memory cached yet):
                    # what a one-shot `nuspacesim run` pays on top of start-up
