@@ -98,16 +98,16 @@ eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
   }
 }
 
-// threads per block of the walk: one warp = one event in flight
-constexpr int walk_block(bool gh) { return gh ? 128 : 32; }
+// threads per block of the walk: one warp = one event in flight, one warp per block (a block
+// ends, and its slot is refilled, with its own event; 4-warp blocks were 4-5 % slower for the
+// Gaisser-Hillas instantiation in round 2)
+constexpr int walk_block(bool) { return 32; }
 
-// Occupancy (measured, tools/ab_bench.sh): left to itself ptxas takes 112-114 registers = 16
-// warps/SM (-4 %); 96 registers, no spills = 20 warps/SM; asking for >= 22 one-warp blocks
-// gives 80 registers = 25 warps/SM: 16 bytes of spill and 1 % faster for the Greisen
-// instantiation, 48 bytes of spill and 2-4 % slower for the Gaisser-Hillas one, which
-// therefore stays at 5 blocks of 4 warps and 96 registers.
+// Occupancy (measured, tools/ab_bench.sh, profiles/r02_ab_kernel_variants.log): 20 one-warp
+// blocks per SM = 96 registers without spills for both instantiations.  22 blocks (80 registers,
+// 100 bytes of spill) is 1.5 % slower, 18 blocks (112 registers) 1.7 % slower.
 template <bool GH>
-__global__ void __launch_bounds__(walk_block(GH), GH ? 5 : 20)
+__global__ void __launch_bounds__(walk_block(GH), 20)
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
                 unsigned long long* __restrict__ stats) {
