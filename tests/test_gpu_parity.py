@@ -487,6 +487,22 @@ def test_mask_scan_and_compaction_ragged(nss):
         _lib.check(L.nss_compact_f64(_lib.ptr(md), _lib.ptr(pos), _lib.ptr(xd), _lib.ptr(out), n,
                                      0, _lib.stream_ptr()))
         assert np.array_equal(out.cpu().numpy(), x[m.astype(bool)])
+        # the multi-column form: one launch, mask and positions read once, per-column scaling
+        ncols = 5
+        X = rng.random((ncols, n))
+        ins = [_lib.to_device(X[c]) for c in range(ncols)]
+        outs = [_lib.empty(k) for _ in range(ncols)]
+        rad = [0, 1, 0, 1, 0]
+        rc = L.nss_compact_columns_f64(
+            _lib.ptr(md), _lib.ptr(pos), (C.c_void_p * ncols)(*[t.data_ptr() for t in ins]),
+            (C.c_void_p * ncols)(*[t.data_ptr() for t in outs]), (C.c_int * ncols)(*rad), ncols,
+            n, _lib.stream_ptr())
+        assert rc == 0
+        for c in range(ncols):
+            want = X[c][m.astype(bool)] * (np.pi / 180.0 if rad[c] else 1.0)
+            assert np.array_equal(outs[c].cpu().numpy(), want), c
+    assert L.nss_compact_columns_f64(None, None, None, None, None, 17, 5, None) == -1  # > 16 columns
+    assert L.nss_compact_columns_f64(None, None, None, None, None, 3, 5, None) == -2
 
 
 def test_cli_run_writes_results(nss, tmp_path):
