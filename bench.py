@@ -249,7 +249,8 @@ def workload_configs(nss):
     from nuspacesim_b200.config import PowerSpectrum, PressureMapCloud
 
     out = {}
-    for tag, le in (("e7", 7.0), ("e9", 9.0), ("e10", 10.0)):
+    for tag, le in (("e7", 7.0), ("e7.5", 7.5), ("e8.5", 8.5), ("e9", 9.0), ("e9.5", 9.5),
+                    ("e10", 10.0)):
         c = nss.NssConfig()
         c.simulation.spectrum.log_nu_energy = le
         out[tag] = (c, f"monospectrum log_nu_energy={le}")
@@ -469,6 +470,15 @@ def main():
             # closed-form radial sums, Gauss rule over wavelengths), so frac can exceed 1.  What
             # the hardware does is in the ncu summary the traffic comes from: issue-slot bound.
             hardware_from_ncu=ncu_traffic.hardware,
+            # live: warp-instructions issued per second by the walk (instructions per event from
+            # that ncu summary x the events this run's launches processed / their CUDA-event
+            # time) against the SM's issue rate (148 SMs x 4 schedulers x the measured clock)
+            issue_slots=(lambda ipe, mhz: None if not ipe or not mhz else dict(
+                achieved=ipe * float(st[0]) / eas_s_per_step, peak=148 * 4 * mhz * 1e6,
+                frac=ipe * float(st[0]) / eas_s_per_step / (148 * 4 * mhz * 1e6),
+                unit="warp-instructions/s"))(
+                (ncu_traffic.hardware or {}).get("warp_instructions_per_event"),
+                clk.get("sm_mhz")),
             hbm_note="acceptance mode has no algorithmic DRAM traffic (0 B/event in, 64 B/step "
                      "out); HBM peak 6535 GB/s (MEASURED_PEAKS.json) bounds only the column-mode "
                      "stages timed in e2e",
@@ -561,10 +571,10 @@ def main():
             clocks=clk, gpu_launches=int(gpu_launches), e2e=e2e,
         )
         line.update(line_extra)
-        if not args.no_workloads:
+        if not args.no_workloads and world == 1:
             line["workloads"] = bench_workloads(nss, torch, n, args.batch,
                                                 first_event(args.warmup + args.steps))
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             port = cpu_baseline(min(args.cpu_seconds, 8.0), cores)
             ref = reference_baseline(args.cpu_seconds, cores)
