@@ -226,7 +226,7 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     return NSS_E_BADARG;
   if (n == 0) return 0;
   if (!beta || !alt || !eshow || !o0 || !o1 || !workspace) return NSS_E_NULL;
-  if (p->eas_profile == 2 && (!u_profile || !g_conex)) return NSS_E_NULL;
+  if (p->eas_profile == 2 && !u_profile) return NSS_E_NULL;
   if (p->has_cloud == 2 && !cloud_ev) return NSS_E_NULL;
   if (p->has_cloud != 2) cloud_ev = nullptr;
   const bool gh = p->eas_profile != 0;
@@ -236,8 +236,13 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
   if ((err = cudaGetDevice(&dev)) != cudaSuccess) return (int)err;
   if (dev < 0 || dev >= MAX_DEVICES) return NSS_E_BADARG;
   int walk_blocks;
+  const double* conex;
+  int conex_rows;
   {
     std::lock_guard<std::mutex> lock(g_init_mutex);
+    conex = g_conex;  // snapshot of the registered table (nss_eas_set_conex_table)
+    conex_rows = g_conex_rows;
+    if (p->eas_profile == 2 && !conex) return NSS_E_NULL;
     if (!g_tables_ready[dev]) {
       nss::EasTables T;
       nss_eas_tables_init(&T);
@@ -273,9 +278,8 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
   if (g1 > 148LL * 64) g1 = 148LL * 64;
   err = cudaMemsetAsync(W.counter, 0, 8, s);
   if (err != cudaSuccess) return (int)err;
-  eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, p->eas_profile, beta, alt, eshow, mask, g_conex,
-                                         g_conex_rows, u_profile, cloud_ev, P.cloud_top, n,
-                                         W.prep);
+  eas_prep_kernel<<<(int)g1, tb, 0, s>>>(mode, p->eas_profile, beta, alt, eshow, mask, conex,
+                                         conex_rows, u_profile, cloud_ev, P.cloud_top, n, W.prep);
 
   const int wpb = walk_block(gh) / 32;  // warps (= events in flight) per block
   long long need = (n + wpb - 1) / wpb;
@@ -333,6 +337,7 @@ extern "C" int nss_eas_set_conex_table(const double* rows_host, int nrows) {
   if (!rows_host) return NSS_E_NULL;
   if (nrows <= 0) return NSS_E_BADARG;
   cudaError_t err;
+  std::lock_guard<std::mutex> lock(g_init_mutex);
   if (g_conex) {
     cudaDeviceSynchronize();
     cudaFree(g_conex);
