@@ -245,6 +245,23 @@ def _gather_rank_sums(row):
     return np.stack([o.cpu().numpy() for o in out])
 
 
+def _slice_bounds(first, last, step):
+    """Slices of about `step` thrown events; with four or more of them the first and the last
+    are quarter-sized: nothing overlaps the first slice's upload or the last slice's download,
+    so those two are kept short."""
+    n = last - first
+    if n <= 0:
+        return []
+    if n < 4 * step or step < 4 or os.environ.get("NSS_SLICE_EDGES", "1") == "0":
+        return [(lo, min(lo + step, last)) for lo in range(first, last, step)]
+    edge = step // 4
+    inner = n - 2 * edge
+    k = -(-inner // step)
+    cuts = [first, first + edge] + [first + edge + (inner * i) // k for i in range(1, k + 1)]
+    cuts.append(last)
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
 class _HostColumns:
     """The full-length host arrays the slices' columns are copied into (utils/host_pool.py:
     page-locked on a helper thread, recycled between calls).  Until the block is ready the
@@ -313,7 +330,7 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     eas = EAS(config, seed=seed)
     U = uniforms or {}
     last = n_thrown if last is None else last
-    bounds = [(lo, min(lo + step, last)) for lo in range(first, last, step)]
+    bounds = _slice_bounds(first, last, step)
     logv(f"Running NuSpaceSim with Energy Spectrum ({config.simulation.spectrum})")
     logv(f"Computing thrown events [{first}, {last}) of {n_thrown} in {len(bounds)} pipelined "
          "slices.")
