@@ -400,7 +400,7 @@ inline TabView view_of(const NssTables* t) {
 // Tau exit-probability table (log10 P over log_e_nu x beta, 25 x 51 float64 = 10.2 KB, plus its
 // two axes) staged in shared memory by the block: the bracket searches and the four gathers of
 // tau_exit_prob_event then hit shared memory instead of L2.  The kernels that use it run a
-// grid of a few blocks per SM (tau_grid) so that one staging pass serves ~2000 events.  The
+// bounded grid (tau_grid) so that one staging pass serves several hundred events.  The
 // CDF grid (25 x 51 x 71 float64 = 724 KB) does not fit the 227 KB of an SM and stays
 // L2-resident.  smem_doubles == 0 (a table too large to stage): global pointers are kept.
 __device__ inline TabView stage_pexit(const TabView& t, double* sm, int smem_doubles) {
@@ -423,10 +423,11 @@ inline int pexit_smem_doubles(const TabView& t) {
   return d * 8 <= 48 * 1024 ? (int)d : 0;
 }
 
-// grid of the table kernels: at most 8 blocks of 256 threads per SM
+// grid of the table kernels: at most 24 blocks of 256 threads per SM (3 resident at 76
+// registers: 8 waves; fewer, longer-lived blocks measured 5-15 % slower, more gain nothing)
 inline int tau_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
-  const int64_t cap = 148LL * 8;
+  const int64_t cap = 148LL * 24;
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Development aid: build libnss_b200 with an alternative nss_eas_core.cuh into gpurun_variants/<name>.so
-#   tools/build_variant.sh <name> <path-to-core-header> [<path-to-nss_eas_kernel.cu>]
+#   tools/build_variant.sh <name> <path-to-core-header> [<path-to-nss_eas_kernel.cu> [<path-to-nss_f64_kernels.cu>]]
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 NAME=$1; HDR=$2
@@ -10,6 +10,7 @@ cp $ROOT/include/nss_b200.h $TMP/include/
 cp $ROOT/nuspacesim_b200/csrc/*.cu $ROOT/nuspacesim_b200/csrc/*.h $TMP/nuspacesim_b200/csrc/
 cp $HDR $TMP/nuspacesim_b200/csrc/nss_eas_core.cuh
 if [ -n "$3" ]; then cp $3 $TMP/nuspacesim_b200/csrc/nss_eas_kernel.cu; fi
+if [ -n "$4" ]; then cp $4 $TMP/nuspacesim_b200/csrc/nss_f64_kernels.cu; fi
 cd $TMP/nuspacesim_b200/csrc
 F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
 nvcc $F -c nss_eas_kernel.cu -o eas.o
