@@ -117,9 +117,14 @@ class PendingColumns:
             dev = torch.cuda.current_device()
 
             def work():
-                torch.cuda.set_device(dev)
-                mm, addr, registered = _new_block(nbytes)
-                self._adopt(mm, addr, registered, nbytes)
+                try:
+                    torch.cuda.set_device(dev)
+                    mm, addr, registered = _new_block(nbytes)
+                    self._adopt(mm, addr, registered, nbytes)
+                except Exception:  # no mapping (address space, memlock limit ...): plain memory
+                    self.pinned = False
+                    self.columns = {nm: torch.empty(self.n, dtype=torch.float64)
+                                    for nm in self.names}
 
             self._thread = threading.Thread(target=work, name="nss-host-columns", daemon=True)
             self._thread.start()
