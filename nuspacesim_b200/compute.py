@@ -312,11 +312,12 @@ def _compute_sliced(config, verbose, output_file, seed, uniforms, sink, n_thrown
     """compute() for large N: the same stage objects, called per slice of thrown events.
 
     Slice k owns thrown events [lo, hi); valid events keep their thrown order, so the result
-    columns are the concatenation of the slices' columns.  Every slice's uniforms are put on
-    the upload stream up front; its columns go to their rows of full-length pinned host
-    arrays on the copy stream while the next slice computes; the five acceptance sums per
-    slice stay on the device until the end and are merged exactly (Chan's update for the sum
-    of squared deviations)."""
+    columns are the concatenation of the slices' columns.  A slice's uniforms are uploaded
+    PREFETCH_SLICES ahead on the upload stream; its throw is enqueued ahead of the previous
+    slice's EAS kernels (the valid-event count is on the host before they finish); its columns
+    go to their rows of full-length page-locked host arrays on the copy stream while the next
+    slice computes; the five acceptance sums per slice stay on the device until the end and
+    are merged exactly (Chan's update for the sum of squared deviations)."""
 
     def logv(*args):
         if verbose:
