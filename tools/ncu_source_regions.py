@@ -15,7 +15,7 @@ REGIONS = [  # (name, text that starts the region in nss_eas_core.cuh)
     ("event setup", "if (E.n_raw <= 0) return;"),
     ("altitude step geometry + grammage + ozone", "const int k = base + lane;"),
     ("prefix sum, AirN, Greisen/GH profile, keep", "const float gincl = gcarry"),
-    ("tail-skip vote and light path", "if (!Ops::any(keep && !(s > 1.0f && may_stop)))"),
+    ("tail-skip vote and light path", "if (!Ops::any(keep && !(s > 1.0f && may_stop"),
     ("per-step: E0, threshold, thetaC, Tfrac, D", "if (s >= 0.4f) {"),
     ("per-step: aerosol + wavelength sum", "if (z < 30.0f) {"),
     ("per-step: spsum, tanC, bin count", "float spsum = (PY * RN) * (acc0 + acc1);"),
