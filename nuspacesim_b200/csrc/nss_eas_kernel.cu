@@ -26,12 +26,16 @@ struct Ops32 {
   static constexpr int W = 32;
   static constexpr unsigned FULL = 0xffffffffu;
   static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+  // inclusive Hillis-Steele scan; the shuffle's own in-range predicate guards the add (no
+  // lane-index compares: 10 instructions)
   static __device__ __forceinline__ float scan_f(float v) {
-    const int l = lane();
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      float t = __shfl_up_sync(FULL, v, d);
-      if (l >= d) v += t;
+      asm volatile("{\n\t.reg .f32 t;\n\t.reg .pred p;\n\t"
+          "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+          "@p add.rn.f32 %0, %0, t;\n\t}"
+          : "+f"(v)
+          : "r"(d));
     }
     return v;
   }
