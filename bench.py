@@ -269,9 +269,11 @@ def workload_configs(nss):
 
 
 def bench_workloads(nss, torch, n, batch, first):
+    """Timed like the headline: the acceptance runner as compute() launches it (work counters
+    compiled out); the counters come from a second, untimed pass over the same events."""
     res = {}
     for name, (cfg, desc) in workload_configs(nss).items():
-        r = nss.AcceptanceRunner(cfg, batch=batch, collect_stats=True)
+        r = nss.AcceptanceRunner(cfg, batch=batch)
         r.enqueue(SEED, first, min(n, batch))  # warm-up (tables, CONEX / cloud map upload)
         torch.cuda.synchronize()
         r.reset()
@@ -281,8 +283,13 @@ def bench_workloads(nss, torch, n, batch, first):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        st = r.stats.cpu().numpy().astype(float)
         mc = r.finalize(r.sums(False))
+        del r
+        rs = nss.AcceptanceRunner(cfg, batch=batch, collect_stats=True)
+        rs.enqueue(SEED, first, n)
+        torch.cuda.synchronize()
+        st = rs.stats.cpu().numpy().astype(float)
+        del rs
         ne = max(st[0], 1.0)
         flops, transc = algorithmic_work(st)
         res[name] = dict(
@@ -292,7 +299,6 @@ def bench_workloads(nss, torch, n, batch, first):
             work_per_eas_event=dict(N_raw=st[1] / ne, N_val=st[2] / ne, J=st[3] / ne,
                                     JNe=st[4] / ne, exp_evaluated=st[5] / ne),
             algorithmic_tflops=flops / (ms * 1e-3) * 1e-12)
-        del r
     return res
 
 

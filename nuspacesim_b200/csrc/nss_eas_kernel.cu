@@ -107,11 +107,25 @@ eas_prep_kernel(int mode, int profile, const double* __restrict__ beta,
 // Gaisser-Hillas instantiation in round 2)
 constexpr int walk_block(bool) { return 32; }
 
-// Occupancy (measured, tools/ab_bench.sh, profiles/r02_ab_kernel_variants.log): 20 one-warp
-// blocks per SM = 96 registers without spills for both instantiations.  22 blocks (80 registers,
-// 100 bytes of spill) is 1.5 % slower, 18 blocks (112 registers) 1.7 % slower.
-template <bool GH>
-__global__ void __launch_bounds__(walk_block(GH), 20)
+// Occupancy (measured, tools/ab_bench.sh, profiles/r02_ab_v20.log).  The instantiations
+// without the work counters -- what compute() and the acceptance runner launch -- fit 72
+// registers (Greisen: 8 bytes of spill) and run 28 one-warp blocks per SM: 1.183e8 events/s
+// against 1.174e8 at 24 blocks (80 registers, no spill), 1.169e8 at 32 (64 registers, 36 bytes)
+// and 1.127e8 at 20 (87 registers).  The instantiations WITH the counters (diagnostics: bench
+// work counters, ncu captures) need 96 registers and stay at 20 blocks.
+#ifndef NSS_LB_G0
+#define NSS_LB_G0 28
+#endif
+#ifndef NSS_LB_G1
+#define NSS_LB_G1 28
+#endif
+constexpr int walk_min_blocks(bool gh, bool stats) {
+  return stats ? 20 : (gh ? NSS_LB_G1 : NSS_LB_G0);
+}
+
+// STATS: with the algorithmic-work counters (stats != nullptr) or with them compiled out
+template <bool GH, bool STATS>
+__global__ void __launch_bounds__(walk_block(GH), walk_min_blocks(GH, STATS))
 eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long long n,
                 nss::EasAcc* __restrict__ acc, unsigned long long* __restrict__ counter,
                 unsigned long long* __restrict__ stats) {
@@ -142,11 +156,11 @@ eas_walk_kernel(nss::EasParams P, const nss::EasPrep* __restrict__ prep, long lo
     }
     nss::EasAcc A;
     const float cloud_top = __shfl_sync(0xffffffffu, ozA_lane, 11);  // EasPrep::cloud
-    nss::eas_walk<Ops32, GH>(c_tables, P, E, ozA_lane, cloud_top, A, stats ? &st : nullptr,
-                             lane == 0);
+    nss::eas_walk<Ops32, GH, STATS>(c_tables, P, E, ozA_lane, cloud_top, A,
+                                    STATS ? &st : nullptr, lane == 0);
     if (lane == 0) acc[i] = A;
   }
-  if (stats && lane == 0 && st.n_events) {
+  if (STATS && stats && lane == 0 && st.n_events) {
     atomicAdd(&stats[0], st.n_events);
     atomicAdd(&stats[1], st.n_raw);
     atomicAdd(&stats[2], st.n_val);
@@ -192,7 +206,7 @@ eas_finish_kernel(int mode, nss::EasParams P, const double* __restrict__ beta,
 constexpr int MAX_DEVICES = 64;
 std::mutex g_init_mutex;
 bool g_tables_ready[MAX_DEVICES] = {};
-int g_walk_blocks[MAX_DEVICES][2] = {};
+int g_walk_blocks[MAX_DEVICES][2][2] = {};  // [device][profile is Gaisser-Hillas][with counters]
 double* g_conex = nullptr;  // device copy of the CONEX Gaisser-Hillas table (registered)
 int g_conex_rows = 0;
 
@@ -254,17 +268,17 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
       if (err != cudaSuccess) return (int)err;
       g_tables_ready[dev] = true;
     }
-    if (g_walk_blocks[dev][gh] == 0) {
+    const bool ws = stats != nullptr;
+    if (g_walk_blocks[dev][gh][ws] == 0) {
       int sms = 0, per_sm = 0;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      err = gh ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<true>,
-                                                               walk_block(true), 0)
-               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eas_walk_kernel<false>,
-                                                               walk_block(false), 0);
+      auto k = gh ? (ws ? eas_walk_kernel<true, true> : eas_walk_kernel<true, false>)
+                  : (ws ? eas_walk_kernel<false, true> : eas_walk_kernel<false, false>);
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, walk_block(gh), 0);
       if (err != cudaSuccess) return (int)err;
-      g_walk_blocks[dev][gh] = sms * (per_sm > 0 ? per_sm : 1);
+      g_walk_blocks[dev][gh][ws] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    walk_blocks = g_walk_blocks[dev][gh];
+    walk_blocks = g_walk_blocks[dev][gh][stats != nullptr];
   }
   const Workspace W = carve(workspace, n);
   nss::EasParams P;
@@ -299,12 +313,9 @@ int launch(int mode, const NssParams* p, const double* beta, const double* alt,
     cudaEventCreate(&rec->b);
     cudaEventRecord(rec->a, s);
   }
-  if (gh)
-    eas_walk_kernel<true><<<blocks, walk_block(true), 0, s>>>(P, W.prep, n, W.acc, W.counter,
-                                                              stats);
-  else
-    eas_walk_kernel<false><<<blocks, walk_block(false), 0, s>>>(P, W.prep, n, W.acc, W.counter,
-                                                                stats);
+  auto walk = gh ? (stats ? eas_walk_kernel<true, true> : eas_walk_kernel<true, false>)
+                 : (stats ? eas_walk_kernel<false, true> : eas_walk_kernel<false, false>);
+  walk<<<blocks, walk_block(gh), 0, s>>>(P, W.prep, n, W.acc, W.counter, stats);
   if (rec) cudaEventRecord(rec->b, s);
   eas_finish_kernel<<<(int)g1, tb, 0, s>>>(mode, P, beta, alt, W.acc, W.prep, n, o0, o1, dph,
                                            cang);

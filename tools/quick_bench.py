@@ -6,9 +6,10 @@ import nuspacesim_b200 as nss
 
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 20
 cfg = nss.NssConfig()
-if len(sys.argv) > 2:  # longitudinal profile, e.g. "Gaisser-Hillas Fluctuated"
+if len(sys.argv) > 2 and sys.argv[2]:  # longitudinal profile, e.g. "Gaisser-Hillas Fluctuated"
     cfg.simulation.eas_long_profile = sys.argv[2]
-r = nss.AcceptanceRunner(cfg, batch=1 << 20, collect_stats=True)
+stats = os.environ.get("NSS_QB_STATS", "1") != "0"  # 0: the path without work counters
+r = nss.AcceptanceRunner(cfg, batch=1 << 20, collect_stats=stats)
 r.enqueue(1234, 0, 1 << 16)
 torch.cuda.synchronize()
 r.reset()
@@ -21,5 +22,6 @@ ms = e0.elapsed_time(e1)
 s = r.sums(False)
 print("n", n, "ms", ms, "events/s", n / ms * 1e3)
 print("sums", s, "result", r.finalize(s))
-st = r.stats.cpu().numpy()
-print("stats per EAS event", st[1:] / max(st[0], 1), "n_eas", st[0])
+if stats:
+    st = r.stats.cpu().numpy()
+    print("stats per EAS event", st[1:] / max(st[0], 1), "n_eas", st[0])
