@@ -840,3 +840,39 @@ def test_eas_entry_points_are_reentrant(nss, eas_large):
         torch.cuda.synchronize()
         for (d0, c0), (d1, c1) in zip(serial, conc):
             assert torch.equal(d0, d1) and torch.equal(c0, c1)
+
+
+@pytest.mark.parametrize("profile", [0, 1, 2])
+def test_walk_with_and_without_work_counters_is_identical(nss, eas_large, profile):
+    """The walk kernel has two instantiations per profile: without the algorithmic-work
+    counters (72 registers, what compute() and the acceptance runner launch) and with them
+    (stats != NULL: bench work counters, ncu captures).  Same source, same arithmetic: the
+    per-event outputs must agree bit for bit, and the counters must be filled."""
+    import ctypes
+
+    from nuspacesim_b200 import _lib
+
+    L = _lib.lib()
+    p = nss.CphotAng(525.0, ["Greisen", "Gaisser-Hillas Parameterized",
+                             "Gaisser-Hillas Fluctuated"][profile]).params
+    ref = eas_large["c1"]
+    x = [_lib.to_device(ref[k][:6000]) for k in ("beta", "alt", "eshow")]
+    n = x[0].numel()
+    u = _lib.to_device(np.random.default_rng(3).random(n)) if profile == 2 else None
+    ws = _lib.eas_workspace(n)
+
+    def run(stats):
+        d, c = _lib.empty(n), _lib.empty(n)
+        rc = L.nss_cphotang(ctypes.byref(p), _lib.ptr(x[0]), _lib.ptr(x[1]), _lib.ptr(x[2]),
+                            _lib.ptr(u), None, n, _lib.ptr(d), _lib.ptr(c), _lib.ptr(stats),
+                            _lib.ptr(ws), _lib.stream_ptr())
+        assert rc == 0
+        return d.cpu().numpy(), c.cpu().numpy()
+
+    st = _lib.zeros(8, "int64")
+    d0, c0 = run(None)
+    d1, c1 = run(st)
+    assert np.array_equal(d0, d1) and np.array_equal(c0, c1)
+    k = st.cpu().numpy()
+    assert k[0] == n and k[2] > 100 * n and k[3] > k[2]  # events, retained steps, radial bins
+    assert (d0 > 0).mean() > 0.9
