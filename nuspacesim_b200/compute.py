@@ -32,7 +32,7 @@ __all__ = ["compute", "run_acceptance"]
 
 
 #: thrown events per slice of compute()'s pipelined path (the acceptance mode's batch size)
-SLICE_EVENTS = 1 << 21
+SLICE_EVENTS = int(os.environ.get("NSS_SLICE_EVENTS", 1 << 21))
 #: slices whose uniforms are uploaded ahead of the one being computed
 PREFETCH_SLICES = 2
 #: enqueue the next slice's throw ahead of the current slice's EAS kernels
@@ -254,7 +254,7 @@ def _slice_bounds(first, last, step):
         return []
     if n < 4 * step or step < 4 or os.environ.get("NSS_SLICE_EDGES", "1") == "0":
         return [(lo, min(lo + step, last)) for lo in range(first, last, step)]
-    edge = step // 4
+    edge = step // int(os.environ.get("NSS_SLICE_EDGE_DIV", 4))
     inner = n - 2 * edge
     k = -(-inner // step)
     cuts = [first, first + edge] + [first + edge + (inner * i) // k for i in range(1, k + 1)]
