@@ -377,7 +377,7 @@ def test_warp_logic_on_host_vs_single_lane(emul, emul32, eas_large, tag):
     rr = rel_err(d32, ref["dphots"][sl])
     assert np.median(rr) < 5e-5 and rr.max() < 2.5e-3
     n_val, n_tail = st[2], st[7]
-    assert 0.005 * n_val < n_tail < 0.25 * n_val, (n_val, n_tail)  # whole chunks of 32 steps
+    assert 0.05 * n_val < n_tail < 0.40 * n_val, (n_val, n_tail)  # whole chunks of 32 steps
 
 
 def test_warp_logic_on_host_gaisser_hillas(emul32, eas_gh):
