@@ -310,14 +310,14 @@ def emul():
     return run
 
 
-@pytest.fixture(scope="module")
-def emul32():
+def _build_emul32(defines=(), tag=""):
     """The walk as a 32-lane warp on the host (tests/host_emul/eas_host_emul32.cpp: one fiber
     per lane, every warp collective a rendezvous).  Returns run(...) -> (d, c, stats8)."""
     src = os.path.join(ROOT, "tests", "host_emul", "eas_host_emul32.cpp")
-    lib = os.path.join(ROOT, "tests", "host_emul", "libeas_host_emul32.so")
+    lib = os.path.join(ROOT, "tests", "host_emul", f"libeas_host_emul32{tag}.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
-                           os.path.join(ROOT, "nuspacesim_b200", "csrc"), src, "-o", lib])
+                           os.path.join(ROOT, "nuspacesim_b200", "csrc"), src, "-o", lib]
+                          + [f"-D{d}" for d in defines])
     L = ctypes.CDLL(lib)
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
@@ -338,6 +338,17 @@ def emul32():
         return d, c, list(st)
 
     return run
+
+
+@pytest.fixture(scope="module")
+def emul32():
+    return _build_emul32()
+
+
+@pytest.fixture(scope="module")
+def emul32_full():
+    """The same 32-lane build with every retained step evaluated (no tail continuation)."""
+    return _build_emul32(["NSS_NO_TAIL_SKIP"], "_full")
 
 
 def test_warp_logic_on_host_cloud_sweep(emul32, golden):
@@ -663,3 +674,39 @@ def test_host_column_pool_recycles_blocks(monkeypatch):
     assert len(H._free) == 2
     H._cleanup()
     assert [c[0] for c in calls].count("unreg") == 2 and not H._free
+
+
+@pytest.mark.parametrize("tag", ["c1", "e9", "pl10"])
+def test_tail_continuation_vs_every_step_evaluated(emul32, emul32_full, eas_large, tag):
+    """The shower tail is continued from the lanes' latest evaluated steps instead of
+    evaluated (nss_eas_core.cuh).  Against the same 32-lane build with
+    every retained step evaluated, on a sample of the reference events: the stated distance
+    (median 7e-8, max 1.4e-6 of the photon density; 2.5e-6 of the Cherenkov angle on 1500
+    events per set) with room for the smaller sample -- and a real share of the steps."""
+    ref = eas_large[tag]
+    idx = np.sort(np.random.default_rng(11).choice(ref["beta"].size, 400, replace=False))
+    b, a, e = ref["beta"][idx], ref["alt"][idx], ref["eshow"][idx]
+    d, c, st = emul32(b, a, e)
+    d0, c0, st0 = emul32_full(b, a, e)
+    assert st0[7] == 0 and st[2] == st0[2]  # same retained steps, none of them continued
+    r = rel_err(d, d0)
+    assert np.median(r) < 2e-7 and np.percentile(r, 99) < 1.5e-6 and r.max() < 3e-6, \
+        (np.median(r), r.max())
+    assert rel_err(c, c0).max() < 5e-6
+    share = st[7] / st[2]
+    assert (0.04 if tag == "pl10" else 0.15) < share < 0.40, share
+
+
+def test_tail_continuation_under_cloud_decks(emul32, emul32_full, golden):
+    """Under a cloud deck the tail IS the signal: the continued steps' weights in the
+    Cherenkov-angle statistics have their own bound (a 12 km deck over a steep shower moved the
+    angle by 1.3e-4 without it)."""
+    sw = golden["eas"]["sweep"]
+    for top in (2.0, 6.0, 12.0):
+        m = (sw[:, 0] == 525.0) & (sw[:, 4] == top)
+        d, c, st = emul32(sw[m, 1], sw[m, 2], sw[m, 3], 525.0, top)
+        d0, c0, _ = emul32_full(sw[m, 1], sw[m, 2], sw[m, 3], 525.0, top)
+        assert np.array_equal(d == 0, d0 == 0)
+        assert rel_err(d, d0).max() < 5e-6 and rel_err(c, c0).max() < 1e-5, \
+            (top, rel_err(d, d0).max(), rel_err(c, c0).max())
+        assert st[7] > 0
