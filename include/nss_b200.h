@@ -163,8 +163,12 @@ int nss_alt_dec(const double* beta, const double* tauBeta, const double* tauLore
  * (S/simulation/eas_optical/shower_properties.py:165).  dphots/cang (optional) are
  * CphotAng's own outputs [photons/m^2, degrees].  stats (optional): 8 device uint64 work
  * counters {events, raw z-steps N_raw, retained steps N_val, radial bins J, J*N_e, exp
- * evaluations in the radial x energy loop, N_val*N_e, tail steps only counted} -- the terms
- * of SURVEY.md 8(d)'s algorithmic-work formula, accumulated over the events that ran.
+ * evaluations in the radial x energy loop, N_val*N_e, tail steps continued instead of
+ * evaluated} -- the terms of SURVEY.md 8(d)'s algorithmic-work formula, accumulated over the
+ * events that ran.  stats != NULL launches the walk instantiation that carries the counters
+ * (96 registers, 20 warps per SM); NULL the one without them (72 registers, 28 warps per SM,
+ * ~8 % faster): same source, results equal to float32 rounding (ptxas fuses multiply-adds per
+ * instantiation; tests/test_gpu_parity.py::test_walk_with_and_without_work_counters_*).
  * workspace: nss_eas_workspace_bytes(n) bytes of device memory (the per-event records the
  * three kernels hand to each other, 144 + 48 bytes per event, and the work counter of the
  * persistent walk kernel); it may be reused by the next call on the SAME stream. */
