@@ -710,3 +710,20 @@ def test_tail_continuation_under_cloud_decks(emul32, emul32_full, golden):
         assert rel_err(d, d0).max() < 5e-6 and rel_err(c, c0).max() < 1e-5, \
             (top, rel_err(d, d0).max(), rel_err(c, c0).max())
         assert st[7] > 0
+
+
+@pytest.mark.parametrize("short,profile", [("ghp", 1), ("ghf", 2)])
+def test_tail_continuation_gaisser_hillas(emul32, emul32_full, eas_gh, short, profile):
+    """The Gaisser-Hillas profiles decay several times more slowly than Greisen's -- 40-50 % of
+    the Fluctuated profile's retained steps are tail -- so their per-step bound is ten times
+    tighter (at Greisen's bound: 7e-5 of the photon density and 3e-5 of the angle on single
+    high-altitude events)."""
+    ref = eas_gh["e10", short]
+    sl = slice(0, 300)
+    args = (ref["beta"][sl], ref["alt"][sl], ref["eshow"][sl], 525.0, None, profile, ref["rows"][sl])
+    d, c, st = emul32(*args)
+    d0, c0, _ = emul32_full(*args)
+    r = rel_err(d, d0)
+    assert np.percentile(r, 99) < 2e-6 and r.max() < 1.5e-5, (np.percentile(r, 99), r.max())
+    assert rel_err(c, c0).max() < 1.5e-5
+    assert 0.15 < st[7] / st[2] < 0.6
