@@ -627,14 +627,27 @@ mc_pass1(const double* cTrN, const double* cNV, const double* cTrV, const double
   block_sum(acc, 4, partial + (size_t)blockIdx.x * MC_NSUM);
 }
 
-// fixed-order sum of the block partials (deterministic), one thread
+// fixed-order sum of one column of the block partials: block 0, 1, 2, ... like a single thread
+// would add them (deterministic, independent of the launch), with the loads of eight blocks
+// in flight at a time
+__device__ __forceinline__ double fold_column(const double* partial, int nblocks, int k) {
+  double s = 0;
+  int b = 0;
+  for (; b + 8 <= nblocks; b += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = partial[(size_t)(b + j) * MC_NSUM + k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; b < nblocks; ++b) s += partial[(size_t)b * MC_NSUM + k];
+  return s;
+}
+
+// one thread per sum (launched with one warp)
 __global__ void mc_fold(const double* partial, int nblocks, int nv, double* out, int out_off) {
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    for (int k = 0; k < nv; ++k) {
-      double s = 0;
-      for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * MC_NSUM + k];
-      out[out_off + k] = s;
-    }
+  const int k = threadIdx.x;
+  if (blockIdx.x == 0 && k < nv) out[out_off + k] = fold_column(partial, nblocks, k);
 }
 
 // pass 2: sum (f - mean)^2 with mean = out[1] / out[3]
@@ -738,14 +751,10 @@ accept_kernel(FrontBufs b, int64_t n, double thr, double sn, double sw, double* 
 }
 
 __global__ void accept_fold(const double* partial, int nblocks, double n_batch, double* out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    for (int k = 0; k < MC_NSUM; ++k) {
-      double s = 0;
-      for (int bl = 0; bl < nblocks; ++bl) s += partial[(size_t)bl * MC_NSUM + k];
-      out[k] += s;
-    }
-    out[5] += n_batch;
-  }
+  const int k = threadIdx.x;
+  if (blockIdx.x != 0) return;
+  if (k < MC_NSUM) out[k] += fold_column(partial, nblocks, k);
+  if (k == MC_NSUM) out[5] += n_batch;
 }
 
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
