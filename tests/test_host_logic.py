@@ -715,9 +715,9 @@ def test_tail_continuation_under_cloud_decks(emul32, emul32_full, golden):
 @pytest.mark.parametrize("short,profile", [("ghp", 1), ("ghf", 2)])
 def test_tail_continuation_gaisser_hillas(emul32, emul32_full, eas_gh, short, profile):
     """The Gaisser-Hillas profiles decay several times more slowly than Greisen's -- 40-50 % of
-    the Fluctuated profile's retained steps are tail -- so their per-step bound is ten times
-    tighter (at Greisen's bound: 7e-5 of the photon density and 3e-5 of the angle on single
-    high-altitude events)."""
+    the Fluctuated profile's retained steps are tail.  The gate on RN / max RN is what keeps
+    showers that start high up from being continued over a long, slowly falling stretch
+    (without it: 7e-5 of the photon density and 3e-5 of the angle on single events)."""
     ref = eas_gh["e10", short]
     sl = slice(0, 300)
     args = (ref["beta"][sl], ref["alt"][sl], ref["eshow"][sl], 525.0, None, profile, ref["rows"][sl])
